@@ -1,0 +1,134 @@
+"""ctypes binding of `libelastic_b200.so` (C ABI declared in include/elastic_b200.h) + the in-tree build recipe.
+
+The reference has no native layer to mirror; this module is the only place where Python touches
+the CUDA library.  There is NO fallback: if the shared object is missing or a call fails, a `NativeError` is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "libelastic_b200.so")
+SOURCES = ["abi.cu", "gather.cu", "epilogue.cu", "tiles.cu"]
+ED_MAX_RENOISE = 64
+ED_F32, ED_F16, ED_BF16 = 0, 1, 2
+FLAG_RENOISE, FLAG_RRG, FLAG_FP16_SEM = 1, 2, 4
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class Plan(C.Structure):
+    """ed_plan_t"""
+    _fields_ = [(n, C.c_int32) for n in
+                ("B", "C", "H", "W", "dH", "dW", "lh", "lw", "g_tp", "g_lp", "nv", "nvr", "nvc", "vh", "vw",
+                 "v_tp", "v_lp", "reserved0")] + \
+               [(n, C.c_void_p) for n in
+                ("row_src", "col_src", "mrow_lo", "mrow_n", "mcol_lo", "mcol_n", "up_row", "up_col", "down_row",
+                 "down_col", "views", "vrow_first", "vrow_cnt", "vcol_first", "vcol_cnt")]
+
+
+class StepParams(C.Structure):
+    """ed_step_params_t"""
+    _fields_ = [("guidance", C.c_float), ("sqrt_beta_t", C.c_float), ("sqrt_alpha_t", C.c_float),
+                ("sqrt_alpha_prev", C.c_float), ("sqrt_dir", C.c_float), ("rrg_weight", C.c_float),
+                ("rrg_norm", C.c_float), ("flags", C.c_int32), ("n_renoise", C.c_int32), ("R1", C.c_int32),
+                ("reserved", C.c_int32 * 2), ("renoise_a", C.c_float * ED_MAX_RENOISE),
+                ("renoise_b", C.c_float * ED_MAX_RENOISE)]
+
+
+class Tiles(C.Structure):
+    """ed_tiles_t"""
+    _fields_ = [(n, C.c_int32) for n in ("ntiles", "ntc", "core", "pad", "scale", "B", "CH", "H", "W", "reserved")] + \
+               [(n, C.c_void_p) for n in ("tiles", "trow_first", "trow_cnt", "tcol_first", "tcol_cnt")]
+
+
+EXPORTS = {
+    "ed_abi_version": (C.c_int, []),
+    "ed_strerror": (C.c_char_p, [C.c_int]),
+    "ed_last_cuda_error": (C.c_int, []),
+    "ed_device_check": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
+    "ed_upload_step_params": (C.c_int, [C.c_void_p, C.POINTER(StepParams), C.c_void_p]),
+    "ed_gather_views": (C.c_int, [C.POINTER(Plan), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "ed_random_pick_gather": (C.c_int, [C.POINTER(Plan), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
+                                        C.c_void_p, C.c_int, C.c_void_p]),
+    "ed_pad_views": (C.c_int, [C.POINTER(Plan), C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "ed_wave_epilogue": (C.c_int, [C.POINTER(Plan), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ed_renoise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "ed_tile_gather": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                 C.c_int, C.c_void_p, C.c_void_p]),
+    "ed_tile_blend": (C.c_int, [C.POINTER(Tiles), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu into libelastic_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    srcs = [os.path.join(_HERE, "csrc", s) for s in SOURCES]
+    deps = srcs + [os.path.join(_HERE, "csrc", "common.cuh"), os.path.join(_ROOT, "include", "elastic_b200.h")]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+           "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(_ROOT, "include"), "-o", LIB_PATH] + srcs
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise NativeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    if verbose:
+        sys.stderr.write(r.stderr)
+    return LIB_PATH
+
+
+def lib():
+    """The loaded shared library (loud failure when absent - there is no CPU / eager fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(the CUDA extension is mandatory, there is no fallback path)")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(l, name)           # AttributeError if the ABI lost a symbol
+            fn.restype, fn.argtypes = res, args
+        if l.ed_abi_version() != 1:
+            raise NativeError("libelastic_b200 ABI version mismatch")
+        _lib = l
+    return _lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        l = lib()
+        msg = l.ed_strerror(status).decode()
+        raise NativeError(f"libelastic_b200 {what}: {msg} (status {status}, cuda error {l.ed_last_cuda_error()})")
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def dtype_code(dt):
+    import torch
+    return {torch.float32: ED_F32, torch.float16: ED_F16, torch.bfloat16: ED_BF16}[dt]
+
+
+def stream_handle():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def strips_array(strips):
+    """4 device pointers (left, right, top, bottom); None -> NULL."""
+    arr = (C.c_void_p * 4)()
+    for i, s in enumerate(strips):
+        arr[i] = s.data_ptr() if s is not None and s.numel() > 0 else None
+    return arr

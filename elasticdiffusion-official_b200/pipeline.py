@@ -1,0 +1,702 @@
+"""`ElasticDiffusion` - drop-in for the reference class of the same name, hot path on hand-written sm_100a kernels.
+
+Boundary: constructor and `generate_image` signatures are identical to
+/root/reference/elastic_diffusion.py:111-115 and :953-965 ("ed:N" below); callers also use `seed_everything`,
+`set_view_config`, `get_downsample_size`, `view_batch_size`, `view_config`, `vae_scale_factor` and the module-level
+`timelog`, `CosineScheduler`, `LinearScheduler`, `ConstScheduler` - all kept.
+
+Design: one denoise step = two *waves*.  All UNet samples of a wave - the 2(R+1) global resampling passes
+and the nv local views - depend only on the wave's input latent and on RNG draws that never depend on UNet outputs,
+so the host replays the reference's exact RNG ledger first (`RngLedger`), one gather kernel pair builds the whole UNet
+batch, PyTorch runs the UNet once (or sharded over ranks), and one fused epilogue kernel turns the outputs into the
+next latent (view scatter + direction fill + CFG + DDIM [+ undo_step] [+ RRG]).
+
+There is no CPU / eager fallback: without the CUDA library or on a non-CUDA device `generate_image` raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import hashlib
+import time
+from contextlib import contextmanager
+from typing import Any
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import native
+from .ddim import DDIMSchedule, check_scheduler, renoise_scalars, step_scalars
+from .geometry import build_geometry, build_tiles, low_res_size, pad_split
+
+try:  # progress bar default of the reference signature (ed:963)
+    from tqdm import tqdm
+except Exception:  # pragma: no cover
+    def tqdm(it, *a, **k):
+        return it
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# module-level API kept from the reference (ed:33-109)
+# ---------------------------------------------------------------------------------------------------------------
+class TimeIt:
+    """Wall-clock accumulator with the reference's interface (ed:33-70)."""
+
+    def __init__(self, sync_gpu=False):
+        self.sync_gpu = sync_gpu
+        self.total_time = {}
+
+    def _tick(self):
+        if self.sync_gpu and torch.cuda.is_available():
+            torch.cuda.synchronize()
+        return time.time()
+
+    def time_function(self, func):
+        def wrapper(*args, **kwargs):
+            t0 = self._tick()
+            out = func(*args, **kwargs)
+            key = f"FUNCTION_{func.__name__}"
+            self.total_time[key] = self.total_time.get(key, 0) + (self._tick() - t0)
+            return out
+        return wrapper
+
+    @contextmanager
+    def time_block(self, block_title):
+        t0 = self._tick()
+        try:
+            yield
+        finally:
+            key = f"BLOCK_{block_title}"
+            self.total_time[key] = self.total_time.get(key, 0) + (self._tick() - t0)
+
+    def print_results(self):
+        for key, spent in self.total_time.items():
+            print(f"{key} took total {spent} seconds to complete.")
+
+
+class LinearScheduler:
+    """RRG weight schedule, ed:73-82."""
+
+    def __init__(self, steps, start_val, stop_val):
+        self.steps, self.start_val, self.stop_val = steps, start_val, stop_val
+
+    def __call__(self, t, *args: Any, **kwds: Any) -> Any:
+        if t >= self.steps:
+            return self.stop_val
+        return self.start_val + (self.stop_val - self.start_val) / self.steps * t
+
+
+class ConstScheduler(LinearScheduler):
+    """ed:85-94."""
+
+    def __call__(self, t, *args: Any, **kwds: Any) -> Any:
+        return self.stop_val if t >= self.steps else self.start_val
+
+
+class CosineScheduler:
+    """ed:96-107."""
+
+    def __init__(self, steps, cosine_scale, factor=0.01):
+        self.steps, self.cosine_scale, self.factor = steps, cosine_scale, factor
+
+    def __call__(self, t, *args: Any, **kwds: Any) -> Any:
+        if t >= self.steps:
+            return 0
+        return self.factor * ((0.5 * (1 + np.cos(np.pi * t / self.steps))) ** self.cosine_scale)
+
+
+timelog = TimeIt(sync_gpu=False)
+
+MODEL_KEYS = {"2.1": "stabilityai/stable-diffusion-2-1-base", "2.0": "stabilityai/stable-diffusion-2-base",
+              "1.5": "runwayml/stable-diffusion-v1-5", "1.4": "CompVis/stable-diffusion-v1-4",
+              "XL1.0": "stabilityai/stable-diffusion-xl-base-1.0"}
+
+
+def _i32(dev, values):
+    return torch.tensor(list(values) if len(values) else [0], dtype=torch.int32, device=dev)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# RNG ledger: the reference's ordered sequence of generator operations, replayed on the host
+# before any kernel of the wave runs.  Only the *order and shape* of draws matter for parity, not where the UNet runs.
+# ---------------------------------------------------------------------------------------------------------------
+class RngLedger:
+    def __init__(self, owner: "ElasticDiffusion", geo):
+        self.o, self.geo = owner, geo
+        self.dev = owner.device
+        self.rng_dev = owner.rng_device if owner.rng_device is not None else owner.device
+        self.strip_cache = {}
+        self.n_cells = geo.lh * geo.lw
+
+    # -- seeds (ed:165-171, 321-324) -----------------------------------------------------------------------------
+    def _seed(self, seed):
+        torch.manual_seed(seed)
+        if self.dev.type == "cuda":
+            torch.cuda.manual_seed(seed)
+
+    @staticmethod
+    def _md5_seed(s):
+        return int(hashlib.md5(s.encode()).hexdigest()[:8], 16)
+
+    def _randn(self, shape, dtype=torch.float32):
+        return torch.randn(shape, device=self.rng_dev, dtype=dtype).to(self.dev)
+
+    def initial_latent(self, shape, dtype):
+        return self._randn(shape, dtype).float()                                   # ed:998
+
+    # -- background strips (ed:327-364); pure function of the id string, cached (the reference's TODO ed:340) ------
+    def _strip(self, h, w, t, tag):
+        if h == 0 or w == 0:
+            return None                                                            # ed:332-333: no generator touched
+        key = f"{tag}_{h}_{w}_{t}"                                                 # same id string as ed:331
+        hit = self.strip_cache.get(key)
+        if hit is None:
+            o = self.o
+            with torch.autocast("cuda", enabled=False):
+                self._seed(self._md5_seed(key))
+                colour = torch.rand(1, 3, device=self.rng_dev).to(self.dev)
+                img = colour[:, :, None, None].repeat(1, 1, h * o.vae_scale_factor, w * o.vae_scale_factor)
+                upcast = o.vae.dtype == torch.float16 and o.vae.config.force_upcast
+                if o.low_vram:
+                    o.vae.to(self.dev)
+                if upcast:
+                    o.upcast_vae()
+                    img = img.float()
+                dist = o.vae.encode(img.to(o.vae.dtype) if not upcast else img).latent_dist
+                if self.rng_dev == self.dev:
+                    z = dist.sample()
+                else:   # test mode (CPU generator): same formula as DiagonalGaussianDistribution.sample
+                    z = dist.mean + dist.std * torch.randn(dist.mean.shape, device=self.rng_dev,
+                                                           dtype=dist.mean.dtype).to(self.dev)
+                z = z * o.vae.config.scaling_factor
+                noise = self._randn(z.shape, z.dtype)
+                hit = o.scheduler.add_noise(z, noise, t.long()).float().contiguous()
+                if upcast:
+                    o.vae.to(dtype=torch.float16)
+            self.strip_cache[key] = hit
+        # every non-empty use consumes one numpy draw and re-keys torch, hit or miss (ed:359)
+        self._seed(int(np.random.randint(100000)))
+        return hit
+
+    def pad_events(self, inner_h, inner_w, t):
+        """Background strips of one padded `unet_step` (ed:405-408, 372-389): width strips first (dim 3), then height
+        strips over the widened tensor (dim 2).  Returns [left, right, top, bottom] (None where empty)."""
+        nat = self.geo.native
+        l, r = pad_split(nat, inner_w)
+        tp, b = pad_split(nat, inner_h)
+        if l + r + tp + b == 0:
+            return [None] * 4
+        left = self._strip(inner_h, l, t, "3_1")
+        right = self._strip(inner_h, r, t, "3_2")
+        wide = inner_w + l + r
+        top = self._strip(tp, wide, t, "2_1")
+        bottom = self._strip(b, wide, t, "2_2")
+        return [left, right, top, bottom]
+
+    # -- per-cell pick indices (ed:502-520, 534-544, 673-675) -------------------------------------------------------
+    def _draw_cells(self, exclude):
+        n = self.n_cells
+        idx = torch.randint(0, 4, (n,))
+        rows = torch.arange(n)
+        rounds = 50
+        bad = exclude[rows, idx]
+        m = int(bad.sum())
+        while m > 0 and rounds > 0:
+            idx[bad] = torch.randint(0, 4, (m,))
+            bad = exclude[rows, idx]
+            m = int(bad.sum())
+            rounds -= 1
+        if m > 0:
+            idx[bad] = torch.randint(0, 4, (m,))
+        return idx
+
+    def global_pass(self, t, resampling_steps, drop_p):
+        """All RNG of one `approximate_latent_direction_w_resampling` call (ed:650-690).
+        Returns (idx uint8 host tensor (R+1, n_cells), strips)."""
+        g = self.geo
+        n = self.n_cells
+        out = torch.zeros(resampling_steps + 1, n, dtype=torch.uint8)
+        exclude = torch.zeros(n, 4, dtype=torch.bool)
+        rows = torch.arange(n)
+        prev = torch.zeros(n, dtype=torch.long)                                    # k = 0: top-left pick (ed:536)
+        strips = None
+        for k in range(resampling_steps + 1):
+            if k > 0:
+                idx = self._draw_cells(exclude)
+                drop = torch.randint(0, 101, (n,), device=self.rng_dev).cpu()      # ed:541
+                drop[drop <= (100 * drop_p)] = 0
+                drop[drop >= (100 * drop_p)] = 1
+                prev = idx * drop + prev * (1 - drop)
+            exclude[rows, prev] = True                                             # ed:675
+            out[k] = prev.to(torch.uint8)
+            strips = self.pad_events(g.lh, g.lw, t)                                # unet_step of this iteration
+        return out, strips
+
+    def local_pass(self, t, view_batch_size):
+        """RNG side effects of `compute_local_uncond_signal` (ed:830-850): one padded unet_step per view chunk."""
+        g = self.geo
+        strips = [None] * 4
+        if g.vh < g.native or g.vw < g.native:
+            for _ in range(0, g.nv, max(1, view_batch_size)):
+                strips = self.pad_events(g.vh, g.vw, t)
+        return strips
+
+    def undo_noise(self, n, shape, out):
+        """The n = num_train/num_inference draws of undo_step (ed:695-701), in order."""
+        for k in range(n):
+            out[k].copy_(torch.randn(shape, device=self.rng_dev, dtype=torch.float32), non_blocking=True)
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class ElasticDiffusion(nn.Module):
+    def __init__(self, device, sd_version='2.0',
+                 verbose=False,
+                 log_freq=5,
+                 view_batch_size=1,
+                 low_vram=False):
+        super().__init__()
+        self._init_common(device, sd_version, verbose, log_freq, view_batch_size, low_vram)
+        print('[INFO] loading stable diffusion...')
+        try:
+            from diffusers import AutoencoderKL, DDIMScheduler, UNet2DConditionModel
+            from transformers import CLIPTextModel, CLIPTextModelWithProjection, CLIPTokenizer
+        except Exception as e:  # diffusers is not part of this image: say so instead of failing obscurely
+            raise ImportError(
+                "ElasticDiffusion(device, sd_version, ...) loads Stable Diffusion through `diffusers` like the "
+                "reference (ed:144-153); `diffusers` is not importable here. Install it, or inject modules with "
+                "ElasticDiffusion.from_components(device, unet=..., vae=..., scheduler=..., text_embeds_fn=...)."
+            ) from e
+        model_key = MODEL_KEYS.get(self.sd_version)
+        if model_key is None:
+            print(f'[INFO] using hugging face custom model key: {self.sd_version}')
+            model_key = self.sd_version
+        home = 'cpu' if self.low_vram else self.device
+        self.vae = AutoencoderKL.from_pretrained(model_key, subfolder="vae", torch_dtype=self.torch_dtype).to(home)
+        self.tokenizer = [CLIPTokenizer.from_pretrained(model_key, subfolder="tokenizer")]
+        self.text_encoder = [CLIPTextModel.from_pretrained(model_key, subfolder="text_encoder",
+                                                           torch_dtype=self.torch_dtype).to(home)]
+        self.unet = UNet2DConditionModel.from_pretrained(model_key, subfolder="unet", torch_dtype=self.torch_dtype).to(home)
+        if self.sd_version == 'XL1.0':
+            self.text_encoder.append(CLIPTextModelWithProjection.from_pretrained(
+                model_key, subfolder="text_encoder_2", torch_dtype=self.torch_dtype).to(home))
+            self.tokenizer.append(CLIPTokenizer.from_pretrained(model_key, subfolder="tokenizer_2"))
+        self.scheduler = DDIMScheduler.from_pretrained(model_key, subfolder="scheduler")
+        self._finish_init()
+        print('[INFO] loaded stable diffusion!')
+
+    # -- construction helpers ---------------------------------------------------------------------------------------
+    def _init_common(self, device, sd_version, verbose, log_freq, view_batch_size, low_vram):
+        self.device = torch.device(device)
+        self.sd_version = sd_version
+        self.verbose = verbose
+        self.torch_dtype = torch.float16 if low_vram else torch.float32            # ed:121
+        self.view_batch_size = view_batch_size
+        self.log_freq = log_freq
+        self.low_vram = low_vram
+        # B200-native knobs (additive; defaults reproduce the reference's behaviour)
+        self.rng_device = None        # None: draw on self.device like the reference; cpu: test mode (CPU goldens)
+        self.autocast = True          # reference runs the loop under torch.autocast('cuda') (ed:1012)
+        self.unet_batch_limit = None  # max samples per UNet call (None: the whole wave in one call)
+        self.dist_group = None        # torch.distributed group to shard wave samples over (None: WORLD if initialised)
+        self.shard_waves = True
+        self.last_run = {}            # counters of the last generate_image call (kernel launches, UNet calls ...)
+        self._text_embeds_fn = None
+        self._projection_dim = None
+
+    def _finish_init(self):
+        for p in self.vae.parameters():                                            # ed:154,173-175
+            p.requires_grad = False
+        self.set_view_config()
+        self.vae_scale_factor = 2 ** (len(self.vae.config.block_out_channels) - 1)  # ed:156
+        check_scheduler(self.scheduler)
+
+    @classmethod
+    def from_components(cls, device, unet, vae, scheduler=None, text_embeds_fn=None, sd_version='2.1',
+                        verbose=False, log_freq=5, view_batch_size=1, low_vram=False, projection_dim=None):
+        """Build from already-instantiated modules (what `__init__` gets from `from_pretrained`, ed:144-153).
+        `text_embeds_fn(prompts) -> (text_embeddings, pooled)` replaces the CLIP encoders (ed:255-265)."""
+        self = cls.__new__(cls)
+        nn.Module.__init__(self)
+        self._init_common(device, sd_version, verbose, log_freq, view_batch_size, low_vram)
+        self.unet, self.vae = unet, vae
+        self.scheduler = scheduler if scheduler is not None else DDIMSchedule()
+        self._text_embeds_fn = text_embeds_fn
+        self._projection_dim = projection_dim
+        self.tokenizer, self.text_encoder = [], []
+        self._finish_init()
+        return self
+
+    # -- small reference API ------------------------------------------------------------------------------------------
+    def set_view_config(self, patch_size=None):
+        """ed:159-163."""
+        ws = patch_size if patch_size is not None else self.unet.config.sample_size // 2
+        self.view_config = {"window_size": ws, "stride": ws}
+        self.view_config["context_size"] = self.unet.config.sample_size - self.view_config["window_size"]
+
+    def seed_everything(self, seed, seed_np=True):
+        """ed:165-171."""
+        torch.manual_seed(seed)
+        if self.device.type == 'cuda':
+            torch.cuda.manual_seed(seed)
+        if seed_np:
+            np.random.seed(seed)
+
+    def requires_grad(self, model, flag=True):
+        for p in model.parameters():
+            p.requires_grad = flag
+
+    def upcast_vae(self):
+        """ed:178-195 (fp16 VAE with force_upcast): decode in fp32."""
+        self.vae.to(dtype=torch.float32)
+
+    def get_downsample_size(self, H, W):
+        """ed:943-950."""
+        return low_res_size(H, W, self.sd_version, self.vae_scale_factor)
+
+    def get_views(self, panorama_height, panorama_width, h_ws=64, w_ws=64, stride=32, **kwargs):
+        """ed:198-229 (pixel sizes in, latent windows out)."""
+        from .geometry import sliding_windows
+        sf = self.vae_scale_factor
+        if panorama_height % sf or panorama_width % sf:
+            raise TypeError(f"height {panorama_height} and Width {panorama_width} must be divisable by {sf}")
+        return sliding_windows(panorama_height // sf, panorama_width // sf, h_ws, w_ws, stride)[0]
+
+    def encoder_prompt(self, prompt, encoder_id):
+        tok = self.tokenizer[encoder_id](prompt, padding='max_length',
+                                         max_length=self.tokenizer[encoder_id].model_max_length,
+                                         truncation=True, return_tensors='pt')
+        return self.text_encoder[encoder_id](tok.input_ids.to(self.device), output_hidden_states=True)
+
+    @torch.no_grad()
+    def get_text_embeds(self, prompt):
+        """ed:255-265."""
+        if self._text_embeds_fn is not None:
+            return self._text_embeds_fn(prompt)
+        if self.sd_version == 'XL1.0':
+            emb = torch.cat([self.encoder_prompt(prompt, 0).hidden_states[-2],
+                             self.encoder_prompt(prompt, 1).hidden_states[-2]], dim=-1)
+            return emb, self.encoder_prompt(prompt, 1)[0]
+        emb = self.encoder_prompt(prompt, 0)[0]
+        return emb, emb
+
+    def _get_add_time_ids(self, original_size, crops_coords_top_left, target_size, dtype):
+        """ed:232-246."""
+        ids = list(original_size + crops_coords_top_left + target_size)
+        proj = self._projection_dim if self._projection_dim is not None else self.text_encoder[1].config.projection_dim
+        passed = self.unet.config.addition_time_embed_dim * len(ids) + proj
+        expected = self.unet.add_embedding.linear_1.in_features
+        if expected != passed:
+            raise ValueError(
+                f"Model expects an added time embedding vector of length {expected}, but a vector of {passed} was "
+                "created. The model has an incorrect config. Please check `unet.config.time_embedding_type` and "
+                "`text_encoder_2.config.projection_dim`.")
+        return torch.tensor([ids], dtype=dtype)
+
+    # -- decode ---------------------------------------------------------------------------------------------------------
+    def decode_latents(self, latents):
+        """ed:267-272."""
+        latents = latents.to(next(iter(self.vae.post_quant_conv.parameters())).dtype)
+        latents = latents / self.vae.config.scaling_factor
+        imgs = self.vae.decode(latents).sample
+        return (imgs / 2 + 0.5).clamp(0, 1)
+
+    def tiled_decode(self, latents, tile_batch=16):
+        """ed:275-310 with the slicing / padding / blending done by ed_tile_gather (TMA, OOB zero fill) and
+        ed_tile_blend; the VAE decoder itself runs through PyTorch, `tile_batch` tiles per call."""
+        self._require_cuda()
+        L = native.lib()
+        latents = latents.float().contiguous()
+        B, C, H, W = latents.shape
+        tg = build_tiles(H, W, self.unet.config.sample_size, self.vae_scale_factor, self.low_vram)
+        dev = latents.device
+        tabs = {k: _i32(dev, v) for k, v in tg.tables.items()}
+        T = tg.core + 2 * tg.pad
+        nt = len(tg.tiles)
+        boxes = torch.empty(nt * B, C, T, T, device=dev, dtype=torch.float32)
+        native.check(L.ed_tile_gather(native.ptr(latents), B, C, H, W, native.ptr(tabs["tiles"]), nt, tg.core, tg.pad,
+                                      native.ptr(boxes), native.stream_handle()), "ed_tile_gather")
+        wdt = next(iter(self.vae.post_quant_conv.parameters())).dtype
+        sf = self.vae_scale_factor
+        patches = None
+        for s in range(0, nt * B, tile_batch):
+            z = boxes[s:s + tile_batch].to(wdt) / self.vae.config.scaling_factor
+            dec = self.vae.decode(z).sample
+            if patches is None:
+                patches = torch.empty(nt * B, dec.shape[1], T * sf, T * sf, device=dev, dtype=dec.dtype)
+            patches[s:s + tile_batch] = dec
+        image = torch.empty(B, patches.shape[1], H * sf, W * sf, device=dev, dtype=torch.float32)
+        tt = native.Tiles(ntiles=nt, ntc=tg.ntc, core=tg.core, pad=tg.pad, scale=sf, B=B, CH=patches.shape[1], H=H, W=W,
+                          tiles=tabs["tiles"].data_ptr(), trow_first=tabs["trow_first"].data_ptr(),
+                          trow_cnt=tabs["trow_cnt"].data_ptr(), tcol_first=tabs["tcol_first"].data_ptr(),
+                          tcol_cnt=tabs["tcol_cnt"].data_ptr())
+        native.check(L.ed_tile_blend(ctypes.byref(tt), native.ptr(patches), native.dtype_code(patches.dtype),
+                                     native.ptr(image), native.stream_handle()), "ed_tile_blend")
+        self.last_run["kernel_launches"] = self.last_run.get("kernel_launches", 0) + 2
+        return image
+
+    # -- the hot path ---------------------------------------------------------------------------------------------------
+    def _require_cuda(self):
+        if self.device.type != "cuda" or not torch.cuda.is_available():
+            raise native.NativeError(
+                "this ElasticDiffusion runs its denoising loop on sm_100a CUDA kernels only (no CPU / eager "
+                f"fallback); got device={self.device}, cuda available={torch.cuda.is_available()}")
+        native.lib()
+
+    def _upload_plan(self, geo):
+        dev = self.device
+        keep = {k: _i32(dev, v) for k, v in geo.tables.items()}
+        lp, rp, tp, bp = geo.g_pad
+        vlp, vrp, vtp, vbp = geo.v_pad
+        plan = native.Plan(B=geo.B, C=geo.C, H=geo.H, W=geo.W, dH=geo.native, dW=geo.native, lh=geo.lh, lw=geo.lw,
+                           g_tp=tp, g_lp=lp, nv=geo.nv, nvr=geo.nvr, nvc=geo.nvc, vh=geo.vh, vw=geo.vw, v_tp=vtp,
+                           v_lp=vlp, **{k: v.data_ptr() for k, v in keep.items()})
+        return plan, keep
+
+    def _dist(self):
+        import torch.distributed as dist
+        if not self.shard_waves or not dist.is_available() or not dist.is_initialized():
+            return None, 0, 1
+        grp = self.dist_group
+        ws = dist.get_world_size(grp)
+        return (grp, dist.get_rank(grp), ws) if ws > 1 else (None, 0, 1)
+
+    def _unet(self, canvas, t, text, pooled, time_ids):
+        """One batched UNet evaluation of a wave (dense part, through PyTorch; ed:417-426 for the XL kwargs).
+        With torch.distributed initialised the samples are sharded over ranks and all-gathered (multi-GPU)."""
+        grp, rank, ws = self._dist()
+        n = canvas.shape[0]
+        if ws > 1:
+            per = (n + ws - 1) // ws
+            lo, hi = min(rank * per, n), min((rank + 1) * per, n)
+        else:
+            per, lo, hi = n, 0, n
+        outs = []
+        limit = self.unet_batch_limit or max(hi - lo, 1)
+        with torch.autocast("cuda", enabled=self.autocast):
+            for s in range(lo, hi, limit):
+                e = min(s + limit, hi)
+                kw = {}
+                if time_ids is not None:
+                    kw["added_cond_kwargs"] = {"text_embeds": pooled[s:e], "time_ids": time_ids[s:e]}
+                outs.append(self.unet(canvas[s:e], t, encoder_hidden_states=text[s:e], **kw)["sample"])
+                self.last_run["unet_calls"] += 1
+                self.last_run["unet_samples"] += e - s
+        if ws == 1:
+            out = outs[0] if len(outs) == 1 else torch.cat(outs)
+            return out.contiguous()
+        import torch.distributed as dist
+        mine = torch.cat(outs) if outs else canvas.new_zeros((0,) + tuple(canvas.shape[1:]))
+        if self._shard_dtype is None:
+            # dtype of the UNet output must agree on every rank, including ranks that got no sample
+            probe = torch.tensor([native.dtype_code(mine.dtype) if mine.numel() else -1], device=self.device)
+            dist.all_reduce(probe, op=dist.ReduceOp.MAX, group=grp)
+            self._shard_dtype = {0: torch.float32, 1: torch.float16, 2: torch.bfloat16}[int(probe.item())]
+        send = torch.zeros((per,) + tuple(canvas.shape[1:]), device=self.device, dtype=self._shard_dtype)
+        send[:hi - lo] = mine
+        gathered = torch.empty((ws * per,) + tuple(canvas.shape[1:]), device=self.device, dtype=self._shard_dtype)
+        dist.all_gather_into_tensor(gathered, send, group=grp)
+        self.last_run["collectives"] += 1
+        return gathered[:n]
+
+    @torch.no_grad()
+    def generate_image(self, prompts, negative_prompts='',
+                       height=768, width=768,
+                       num_inference_steps=50,
+                       guidance_scale=10.0,
+                       resampling_steps=20,
+                       new_p=0.3, rrg_stop_t=0.2,
+                       rrg_init_weight=1000,
+                       rrg_scherduler_cls=CosineScheduler,
+                       cosine_scale=3.0,
+                       repaint_sampling=True,
+                       progress=tqdm,
+                       tiled_decoder=False,
+                       grid=False):
+        latent, image_log = self.denoise(prompts, negative_prompts, height, width, num_inference_steps, guidance_scale,
+                                         resampling_steps, new_p, rrg_stop_t, rrg_init_weight, rrg_scherduler_cls,
+                                         cosine_scale, repaint_sampling, progress)
+        # ---- decode (ed:1080-1130) ------------------------------------------------------------------------------------
+        needs_upcasting = self.vae.dtype == torch.float16 and self.vae.config.force_upcast
+        if self.low_vram:
+            self.unet.cpu()
+            self.vae.to(self.device)
+        if needs_upcasting:
+            self.upcast_vae()
+        decode_fn = self.tiled_decode if tiled_decoder else self.decode_latents
+        if self.verbose and self._x0_log:
+            x0s = torch.cat([decode_fn(z.to(self.device)) for z in self._x0_log]).clip(0, 1)
+            image_log['intermediate_x0_imgs'] = _to_pil(_grid(x0s))
+        imgs = torch.cat([decode_fn(latent[i:i + 1]) for i in range(len(latent))])   # ed:1121 (one sample at a time)
+        if grid:
+            imgs = [_grid(imgs)]
+        imgs = [_to_pil(img) for img in imgs]
+        if needs_upcasting:
+            self.vae.to(dtype=torch.float16)
+        return imgs, image_log
+
+    @torch.no_grad()
+    def denoise(self, prompts, negative_prompts='', height=768, width=768, num_inference_steps=50,
+                guidance_scale=10.0, resampling_steps=20, new_p=0.3, rrg_stop_t=0.2, rrg_init_weight=1000,
+                rrg_scherduler_cls=CosineScheduler, cosine_scale=3.0, repaint_sampling=True, progress=tqdm,
+                step_callback=None):
+        """The loop of ed:967-1078.  Returns (final latent (B,4,H/8,W/8) fp32 on device, image_log)."""
+        self._require_cuda()
+        L = native.lib()
+        sf = self.vae_scale_factor
+        if height % sf or width % sf:
+            raise TypeError(f"height {height} and Width {width} must be divisable by {sf}")   # ed:200-201 raises a str
+        self.last_run = dict(kernel_launches=0, unet_calls=0, unet_samples=0, collectives=0, vae_encodes=0, steps=0)
+        self._shard_dtype = None
+        self._x0_log = []
+        ds = self.get_downsample_size(height, width)                                           # ed:968
+        self.default_size = (4 * height, 4 * width)                                            # ed:969
+        T = num_inference_steps
+        n_rrg = T - int(T * rrg_stop_t)
+        if rrg_scherduler_cls == CosineScheduler:                                              # ed:972-979
+            rrg_w = rrg_scherduler_cls(steps=n_rrg, cosine_scale=cosine_scale, factor=rrg_init_weight)
+        else:
+            rrg_w = rrg_scherduler_cls(steps=n_rrg, start_val=rrg_init_weight, stop_val=0)
+        if isinstance(prompts, str):
+            prompts = [prompts]
+        if isinstance(negative_prompts, str):
+            negative_prompts = [negative_prompts] * len(prompts)
+        if self.low_vram:
+            self.vae.cpu()
+            self.unet.cpu()
+            self.text_encoder = [e.to(self.device) for e in self.text_encoder]
+        un_text, un_pool = self.get_text_embeds(negative_prompts)                              # ed:992-993
+        co_text, co_pool = self.get_text_embeds(prompts)
+        un_text, un_pool, co_text, co_pool = (z.to(self.device) for z in (un_text, un_pool, co_text, co_pool))
+
+        B, C = len(prompts), self.unet.config.in_channels
+        H, W = height // sf, width // sf
+        is_xl = self.sd_version.startswith('XL')
+        native_size = 128 if is_xl else 64                                                     # ed:398-400
+        vc = self.view_config
+        geo = build_geometry(B, C, H, W, native_size, ds, vc["window_size"], vc["stride"], vc["context_size"])
+        if (geo.lh, geo.lw) != tuple(ds):
+            raise ValueError(f"resampler produced {geo.lh}x{geo.lw}, expected {ds}")
+        plan, _keep = self._upload_plan(geo)
+        ledger = RngLedger(self, geo)
+        dev = self.device
+
+        x = ledger.initial_latent((B, C, H, W), self.torch_dtype)                               # ed:998
+        self.scheduler.set_timesteps(T)                                                        # ed:1001
+        ts = self.scheduler.timesteps
+        if self.low_vram:
+            self.text_encoder = [e.cpu() for e in self.text_encoder]
+            self.vae.cpu()
+            self.unet.to(dev)
+
+        R = resampling_steps
+        n_re = self.scheduler.config.num_train_timesteps // T
+        if n_re > native.ED_MAX_RENOISE:
+            raise ValueError(f"undo_step needs {n_re} forward steps > ED_MAX_RENOISE={native.ED_MAX_RENOISE}")
+        nv = geo.nv
+        # static per-call buffers (addresses fixed for the whole loop)
+        in_dtype = torch.float32
+        n1, n2 = 2 * B * (R + 1) + nv * B, 2 * B + nv * B
+        canvas = torch.empty(max(n1, n2), C, native_size, native_size, device=dev, dtype=in_dtype)
+        x_mid, x_next = torch.empty_like(x), torch.empty_like(x)
+        x0_buf = torch.empty_like(x) if self.verbose else None
+        noise = torch.empty(n_re, B, C, H, W, device=dev, dtype=torch.float32)
+        idx1 = torch.empty(R + 1, geo.lh * geo.lw, device=dev, dtype=torch.uint8)
+        idx2 = torch.zeros(1, geo.lh * geo.lw, device=dev, dtype=torch.uint8)
+        d_params = torch.empty(2, ctypes.sizeof(native.StepParams), device=dev, dtype=torch.uint8)
+        text_pair, pool_pair = torch.cat([un_text, co_text]), torch.cat([un_pool, co_pool], dim=0)   # ed:996-997
+        text1 = torch.cat([text_pair] * (R + 1) + [un_text] * nv)
+        pool1 = torch.cat([pool_pair] * (R + 1) + [un_pool] * nv)
+        text2 = torch.cat([text_pair] + [un_text] * nv)
+        pool2 = torch.cat([pool_pair] + [un_pool] * nv)
+        time_ids = None
+        if is_xl:                                                                              # ed:413-420, hoisted
+            time_ids = self._get_add_time_ids(self.default_size, (0, 0), self.default_size, dtype=text_pair.dtype)
+            time_ids = time_ids.to(dev).repeat(max(n1, n2), 1)
+        rrg_norm = float(torch.tensor(2.0 / (C * H * W), dtype=torch.float64).to(torch.float32))
+        image_log = {}
+
+        def run_wave(x_in, t, idx_dev, R1, strips_g, strips_v, prm, slot, noise_buf, x_out, x0_out, text, pool):
+            st = native.stream_handle()
+            n = 2 * B * R1 + nv * B
+            cv = canvas[:n]
+            native.check(L.ed_random_pick_gather(ctypes.byref(plan), R1, native.ptr(x_in), native.ptr(idx_dev),
+                                                 native.strips_array(strips_g), native.ptr(cv),
+                                                 native.dtype_code(cv.dtype), st), "ed_random_pick_gather")
+            native.check(L.ed_gather_views(ctypes.byref(plan), native.ptr(x_in), native.ptr(cv),
+                                           native.dtype_code(cv.dtype), 2 * B * R1, st), "ed_gather_views")
+            self.last_run["kernel_launches"] += 2
+            if any(s is not None for s in strips_v):
+                native.check(L.ed_pad_views(ctypes.byref(plan), native.strips_array(strips_v), native.ptr(cv),
+                                            native.dtype_code(cv.dtype), 2 * B * R1, st), "ed_pad_views")
+                self.last_run["kernel_launches"] += 1
+            out = self._unet(cv, t, text[:n], pool[:n], None if time_ids is None else time_ids[:n])
+            if out.dtype == torch.float16:
+                prm.flags |= native.FLAG_FP16_SEM
+            native.check(L.ed_upload_step_params(native.ptr(d_params[slot]), ctypes.byref(prm), st), "upload")
+            native.check(L.ed_wave_epilogue(ctypes.byref(plan), native.ptr(d_params[slot]), native.ptr(x_in),
+                                            native.ptr(out), native.dtype_code(out.dtype), native.ptr(idx_dev),
+                                            native.ptr(noise_buf), native.ptr(x_out), native.ptr(x0_out), st),
+                         "ed_wave_epilogue")
+            self.last_run["kernel_launches"] += 1
+            return out
+
+        for i, t in enumerate(progress(ts)):
+            last = i == len(ts) - 1
+            repaint = bool(repaint_sampling and R > 0 and not last)                            # ed:1038
+            w = rrg_w(i)
+            rrg_on = w > 10                                                                    # ed:1062
+            sc = step_scalars(self.scheduler, t)
+
+            # ---- RNG ledger of the step, in the reference's order (Appendix B of SURVEY.md) -----------------------------
+            idx_host, strips_g = ledger.global_pass(t, R, 1 - new_p)                            # ed:1016
+            strips_v = ledger.local_pass(t, self.view_batch_size)                               # ed:1027
+            idx1.copy_(idx_host)
+            if repaint:
+                ledger.undo_noise(n_re, (B, C, H, W), noise)                                   # ed:1040
+                _, strips_g2 = ledger.global_pass(t, 0, 1 - new_p)                              # ed:1043
+                strips_v2 = ledger.local_pass(t, self.view_batch_size)                          # ed:1049
+
+            # ---- wave 1 ----------------------------------------------------------------------------------------------------
+            prm = native.StepParams(guidance=guidance_scale, rrg_weight=float(w), rrg_norm=rrg_norm, R1=R + 1, **sc)
+            if repaint:
+                a, b = renoise_scalars(self.scheduler, ts[i + 1])
+                prm.flags = native.FLAG_RENOISE
+                prm.n_renoise = n_re
+                for k in range(n_re):
+                    prm.renoise_a[k], prm.renoise_b[k] = a[k], b[k]
+                run_wave(x, t, idx1, R + 1, strips_g, strips_v, prm, 0, noise, x_mid, None, text1, pool1)
+                # ---- wave 2 (repaint: one more estimate at the re-noised latent, guidance / 3; ed:1041-1056) --------
+                prm2 = native.StepParams(guidance=guidance_scale / 3, rrg_weight=float(w), rrg_norm=rrg_norm, R1=1, **sc)
+                prm2.flags = native.FLAG_RRG if rrg_on else 0
+                run_wave(x_mid, t, idx2, 1, strips_g2, strips_v2, prm2, 1, None, x_next, x0_buf, text2, pool2)
+            else:
+                prm.flags = native.FLAG_RRG if rrg_on else 0
+                run_wave(x, t, idx1, R + 1, strips_g, strips_v, prm, 0, None, x_next, x0_buf, text1, pool1)
+            x, x_next = x_next, x                                                              # ed:1078
+            self.last_run["steps"] += 1
+            if self.verbose and i % self.log_freq == 0:
+                self._x0_log.append(x0_buf.clone().cpu())
+            if step_callback is not None:
+                step_callback(i, x)
+        self.last_run["vae_encodes"] = len(ledger.strip_cache)
+        return x, image_log
+
+
+def _grid(imgs):
+    """make_grid(imgs, nrow=8, padding=2) equivalent for the small logging grids of ed:1099-1124."""
+    n, c, h, w = imgs.shape
+    cols = min(8, n)
+    rows = (n + cols - 1) // cols
+    out = imgs.new_zeros(c, rows * (h + 2) + 2, cols * (w + 2) + 2)
+    for k in range(n):
+        r, q = divmod(k, cols)
+        out[:, 2 + r * (h + 2):2 + r * (h + 2) + h, 2 + q * (w + 2):2 + q * (w + 2) + w] = imgs[k]
+    return out
+
+
+def _to_pil(img):
+    """torchvision ToPILImage for a float CHW tensor in [0,1]: mul(255).byte() (ed:1125)."""
+    from PIL import Image
+    arr = img.detach().float().cpu().mul(255).byte().permute(1, 2, 0).numpy()
+    return Image.fromarray(arr[:, :, 0] if arr.shape[2] == 1 else arr)

@@ -1,0 +1,174 @@
+/*
+ * elastic_b200.h - C ABI of the B200-native ElasticDiffusion hot path (libelastic_b200.so, sm_100a).
+ *
+ * The reference (MoayedHajiAli/ElasticDiffusion-official) is 100 % Python/PyTorch: it has NO plugin / FFI / C-ABI
+ * (SURVEY.md section 8b).  The drop-in boundary is the Python class `ElasticDiffusion.generate_image`
+ * (reference elastic_diffusion.py:952-1130, "ed:N" below); this header defines the native op set that the new
+ * `generate_image` calls underneath it.  Every entry point below names the chain of reference ops it replaces.
+ *
+ * Conventions
+ *   - plain C linkage, raw DEVICE pointers + sizes, no torch types; `stream` is a cudaStream_t passed as void*.
+ *   - no allocation, no synchronisation, no host<->device copies inside (CUDA-graph capturable), except the
+ *     explicit ed_upload_* helper which is a cudaMemcpyAsync.
+ *   - returns ED_OK (0) or a negative ed_status; ed_strerror() gives the text.  CUDA launch errors are returned as
+ *     ED_ERR_CUDA with the cudaError_t retrievable through ed_last_cuda_error().
+ *   - all latents are contiguous NCHW; "canvas" = one UNet sample of native size (C, dH, dW).
+ *
+ * Wave sample layout (one UNet batch per wave):
+ *     sample(k, s, b) = (k*2 + s)*B + b      k = resampling iteration 0..R, s = 0 uncond / 1 cond   (ed:436-439)
+ *     sample(view v, b) = 2*B*(R+1) + v*B + b                                                         (ed:845)
+ */
+#ifndef ELASTIC_B200_H_
+#define ELASTIC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ED_ABI_VERSION 1
+#define ED_MAX_RENOISE 64
+
+typedef enum {
+  ED_OK = 0,
+  ED_ERR_INVALID = -1,     /* bad argument (null pointer, negative size, unsupported dtype ...) */
+  ED_ERR_UNSUPPORTED = -2, /* shape outside what the kernel handles (message says which) */
+  ED_ERR_CUDA = -3,        /* CUDA runtime / driver error, see ed_last_cuda_error() */
+  ED_ERR_NO_DEVICE = -4    /* no sm_100 device / driver present */
+} ed_status;
+
+typedef enum { ED_F32 = 0, ED_F16 = 1, ED_BF16 = 2 } ed_dtype;
+
+/* Static geometry of one generate_image call ("plan"): built once on the host from the reference's integer logic
+ * (get_views ed:198-229, crop_with_context ed:706-757, random_nearest_downsample tables ed:568-611,
+ * restore_mask_shape ed:446-465, F.interpolate(nearest) index maps ed:636,688,922).  All pointers are DEVICE
+ * pointers to int32 tables that stay alive for the whole call. */
+typedef struct {
+  int32_t B, C, H, W;       /* latent (B,C,H,W) fp32 */
+  int32_t dH, dW;           /* UNet native canvas (64 or 128, ed:398-400) */
+  int32_t lh, lw;           /* low-res (resampled) latent size */
+  int32_t g_tp, g_lp;       /* top/left offset of the low-res latent inside the canvas (ed:405-406) */
+  int32_t nv, nvr, nvc;     /* number of views, view-grid rows, view-grid cols (view i = r*nvc + c) */
+  int32_t vh, vw;           /* view crop size (window + context), same for all views */
+  int32_t v_tp, v_lp;       /* top/left offset of a view crop inside the canvas (0 unless view < native) */
+  int32_t reserved0;
+  const int32_t* row_src;   /* [2*lh] latent row feeding each row of the 2x-resized grid (ed:585-589,612) */
+  const int32_t* col_src;   /* [2*lw] */
+  const int32_t* mrow_lo;   /* [H] first resized row OR-ed into latent row y of the restored mask (ed:446-465) */
+  const int32_t* mrow_n;    /* [H] how many (0,1,2) */
+  const int32_t* mcol_lo;   /* [W] */
+  const int32_t* mcol_n;    /* [W] */
+  const int32_t* up_row;    /* [H]  low-res row read by nearest-upsampling to row y (ed:636,922) */
+  const int32_t* up_col;    /* [W] */
+  const int32_t* down_row;  /* [lh] full-res row read by nearest-downsampling (ed:688) */
+  const int32_t* down_col;  /* [lw] */
+  const int32_t* views;     /* [nv*8] h0,h1,w0,w1 (window), r0,c0 (crop origin), n_t,n_l (window offset in crop) */
+  const int32_t* vrow_first;/* [H] first view-grid row whose window covers latent row y */
+  const int32_t* vrow_cnt;  /* [H] number of consecutive covering view-grid rows */
+  const int32_t* vcol_first;/* [W] */
+  const int32_t* vcol_cnt;  /* [W] */
+} ed_plan_t;
+
+/* Per-wave scalars, read by the epilogue kernel from DEVICE memory so that a captured CUDA graph can be replayed
+ * with new values (upload with ed_upload_step_params or any memcpy). */
+typedef struct {
+  float guidance;           /* g of eps = uncond + g*direction (ed:1031,1053) */
+  float sqrt_beta_t;        /* (1 - abar_t)^0.5   DDIM, diffusers 0.21.4 scheduling_ddim.step */
+  float sqrt_alpha_t;       /* abar_t^0.5 */
+  float sqrt_alpha_prev;    /* abar_prev^0.5 */
+  float sqrt_dir;           /* (1 - abar_prev)^0.5  (eta = 0) */
+  float rrg_weight;         /* fp32(rrg_scheduler(i))  (ed:1062-1071) */
+  float rrg_norm;           /* fp32(2 / (C*H*W))  mse_loss backward, reduction=mean (ed:932) */
+  int32_t flags;            /* ED_FLAG_* */
+  int32_t n_renoise;        /* forward steps of undo_step (ed:693), <= ED_MAX_RENOISE */
+  int32_t R1;               /* resampling iterations in this wave = resampling_steps+1 (ed:661) */
+  int32_t reserved[2];
+  float renoise_a[ED_MAX_RENOISE]; /* (1-beta_{t+i})^0.5 (ed:702) */
+  float renoise_b[ED_MAX_RENOISE]; /* beta_{t+i}^0.5 */
+} ed_step_params_t;
+
+#define ED_FLAG_RENOISE 1   /* out_latent = undo_step(x_prev) (ed:1039-1040) */
+#define ED_FLAG_RRG 2       /* out_latent = x_prev + reduced_resolution_guidance(...) (ed:1062-1078) */
+#define ED_FLAG_FP16_SEM 4  /* emulate the fp16 roundings of the reference's CUDA-autocast path (ed:655,1031) */
+
+/* ---- library / device ------------------------------------------------------------------------------------- */
+int ed_abi_version(void);
+const char* ed_strerror(int status);
+int ed_last_cuda_error(void);
+/* ED_OK when device `dev` exists and is compute capability 10.x; writes the SM count. */
+int ed_device_check(int dev, int* sm_count);
+/* cudaMemcpyAsync(host -> device) of one ed_step_params_t (host buffer must stay valid until the copy ran). */
+int ed_upload_step_params(void* d_params, const ed_step_params_t* h_params, void* stream);
+
+/* ---- K1: view gather (TMA)  -- replaces crop_with_context x views + torch.cat, ed:834-845, 706-757 ------------
+ * Copies, for every view v, batch b, channel c, the contiguous box latent[b,c, r0:r0+vh, c0:c0+vw] into
+ * canvas sample(view v, b) at offset (v_tp, v_lp).  fp32 -> fp32 goes through TMA tensor-map box loads/stores
+ * (UTMALDG/UTMASTG); other output dtypes or TMA-incompatible strides use a vectorised LDG/STG kernel.
+ * `first_sample` = index of sample(view 0, b 0) inside `canvas`. */
+int ed_gather_views(const ed_plan_t* plan, const float* latent, void* canvas, int canvas_dtype,
+                    int first_sample, void* stream);
+
+/* ---- K3/K9: random-pick gather + background pad -- replaces random_nearest_downsample / random_downsample
+ * (ed:523-630: nearest 2x upsample, row/col select, 4x F.unfold, advanced index) and the torch.cat of
+ * background_pad (ed:366-391) for all R+1 resampling iterations of a wave at once.
+ *   idx      [R1][lh*lw] uint8 : which of the 4 pixels of each 2x2 cell was drawn (ed:534-544)
+ *   strips   4 device pointers (left,right,top,bottom) to fp32 (1,C,h,w) background strips or NULL (ed:379-387);
+ *            left/right are (C, lh, l_p / r_p), top/bottom are (C, t_p / b_p, dW)
+ * Writes sample(k,0,b) and sample(k,1,b) (the reference feeds cat([x]*2), ed:436). */
+int ed_random_pick_gather(const ed_plan_t* plan, int R1, const float* latent, const uint8_t* idx,
+                          const float* const strips[4], void* canvas, int canvas_dtype, void* stream);
+
+/* background strips for view samples smaller than the native size (window collapse, ed:820-825 + ed:405-408) */
+int ed_pad_views(const ed_plan_t* plan, const float* const strips[4], void* canvas, int canvas_dtype,
+                 int first_sample, void* stream);
+
+/* ---- K2+K5+K6(+K7)(+K8): fused wave epilogue ---------------------------------------------------------------
+ * One pass over the full-resolution latent that replaces
+ *   - first-writer-wins view scatter                        compute_local_uncond_signal ed:852-861
+ *   - direction = cond - uncond, nearest-up, masked fill over R+1 iterations, NaN back-fill
+ *                                                           ed:439-440, 634-647, 661-681
+ *   - eps = uncond + g*direction, DDIM x0 / x_prev          ed:1031-1035, 1053-1056 (+ diffusers step)
+ *   - flags & ED_FLAG_RENOISE: undo_step                    ed:692-704 (noise = n_renoise torch-drawn tensors)
+ *   - flags & ED_FLAG_RRG: reduced-resolution guidance      ed:886-940 and global_latent = nxt + cascade ed:1078
+ * unet_out  (n_samples, C, dH, dW) of dtype out_dtype in the wave sample layout
+ * noise     [n_renoise][B*C*H*W] fp32 or NULL
+ * out_latent / out_x0 fp32 (B,C,H,W); out_x0 may be NULL. */
+int ed_wave_epilogue(const ed_plan_t* plan, const ed_step_params_t* d_params, const float* latent,
+                     const void* unet_out, int out_dtype, const uint8_t* idx, const float* noise,
+                     float* out_latent, float* out_x0, void* stream);
+
+/* ---- K7 alone: x <- a_k*x + b_k*eps_k, k = 0..n-1 in sequence (ed:692-704) ---------------------------------- */
+int ed_renoise(const ed_step_params_t* d_params, const float* x, const float* noise, float* out,
+               int64_t numel, void* stream);
+
+/* ---- K10: tiled decode glue -- replaces F.pad + per-tile slicing/cat (ed:287-300) and the accumulate /
+ * count / divide blend (ed:303-308) -----------------------------------------------------------------------------
+ * Tile table (DEVICE int32): tiles[j*4 .. j*4+3] = h0,h1,w0,w1 of core tile j in latent units, row-major tile grid
+ * (get_views(core, core, stride), ed:287).
+ * ed_tile_gather: out[(j*B+b), c, :, :] = zero-padded latent box of side T = core+2*pad around tile j.
+ *                 fp32 TMA box loads with out-of-bounds zero fill (== F.pad(..., 'constant', 0), ed:289). */
+int ed_tile_gather(const float* latent, int B, int C, int H, int W, const int32_t* tiles_dev, int ntiles, int core,
+                   int pad, float* out, void* stream);
+
+typedef struct {
+  int32_t ntiles, ntc;        /* number of tiles, tile-grid columns (tile j = r*ntc + c) */
+  int32_t core, pad, scale;   /* latent units; scale = vae_scale_factor (8) */
+  int32_t B, CH, H, W;        /* image batch, image channels (3), latent H, W */
+  int32_t reserved;
+  const int32_t* tiles;       /* [ntiles*4] */
+  const int32_t* trow_first;  /* [H] first tile-grid row covering latent row y, and count (consecutive) */
+  const int32_t* trow_cnt;
+  const int32_t* tcol_first;  /* [W] */
+  const int32_t* tcol_cnt;
+} ed_tiles_t;
+
+/* ed_tile_blend: image[b,ch,y,x] = ( sum over covering tiles j, ascending, of clamp(patch_j/2 + 0.5, 0, 1) ) / count
+ *   patches (ntiles*B, CH, T*scale, T*scale) raw VAE decoder output of dtype patch_dtype (decode_latents' /2+.5
+ *   and clamp, ed:271, are fused here); image (B, CH, H*scale, W*scale) fp32. */
+int ed_tile_blend(const ed_tiles_t* tiles, const void* patches, int patch_dtype, float* image, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ELASTIC_B200_H_ */

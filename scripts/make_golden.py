@@ -1,0 +1,70 @@
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference (/root/reference/elastic_diffusion.py) through
+oracle/ref_shim.py on CPU fp32 with the synthetic StubUNet / StubVAE (fixed seeds).
+
+Run in the build container only (the reference does not exist on the GPU box):
+    python scripts/make_golden.py
+Each fixture holds the call's kwargs, the final latent handed to the VAE (ed:1121) and coarse image statistics.
+"""
+import importlib
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+syn = importlib.import_module("elasticdiffusion-official_b200.synthetic")
+from oracle.ddim_restated import DDIMRestated  # noqa: E402
+from oracle.ref_shim import build_reference, run_reference  # noqa: E402
+
+# name -> (sd_version, view_batch_size, generate_image kwargs).  BASELINE.json configs at reduced step counts.
+CASES = {
+    "sd15_512x512_T5_R3": ("1.5", 1, dict(height=512, width=512, num_inference_steps=5, resampling_steps=3)),
+    "sd15_512x512_T3_R0": ("1.5", 1, dict(height=512, width=512, num_inference_steps=3, resampling_steps=0)),
+    "sd21_512x1024_T4_R4": ("2.1", 8, dict(height=512, width=1024, num_inference_steps=4, resampling_steps=4)),
+    "sd21_512x1024_B2_T3_R2": ("2.1", 2, dict(height=512, width=1024, num_inference_steps=3, resampling_steps=2,
+                                               prompts=["a cat", "a dog on a bench"])),
+    "sd21_640x896_T3_R2_norepaint": ("2.1", 2, dict(height=640, width=896, num_inference_steps=3, resampling_steps=2,
+                                                    repaint_sampling=False, cosine_scale=3.0)),
+    "xl_1024x2048_T3_R7": ("XL1.0", 16, dict(height=1024, width=2048, num_inference_steps=3, resampling_steps=7)),
+    "xl_2048x2048_T2_R2_tiled": ("XL1.0", 16, dict(height=2048, width=2048, num_inference_steps=2, resampling_steps=2,
+                                                   tiled_decoder=True)),
+    "xl_1536x1536_T2_R3": ("XL1.0", 16, dict(height=1536, width=1536, num_inference_steps=2, resampling_steps=3)),
+    "xl_1080x1920_T2_R2": ("XL1.0", 4, dict(height=1080, width=1920, num_inference_steps=2, resampling_steps=2)),
+}
+DEFAULTS = dict(prompts="a cat", negative_prompts="blurry", guidance_scale=10.0, new_p=0.3, rrg_stop_t=0.2,
+                rrg_init_weight=1000, cosine_scale=10, repaint_sampling=True)
+SEED = 0
+
+
+def components(sd):
+    xl = sd.startswith("XL")
+    unet = syn.StubUNet(sample_size=128 if xl else 64, cross_dim=16, xl=xl, pooled_dim=8)
+    return unet, syn.StubVAE(), syn.StubTextEncoder(16, 8 if xl else None), (8 if xl else None)
+
+
+def image_stats(img):
+    """3 x 16 x 16 block means of the PIL image as float tensor (cheap stand-in for the full image)."""
+    import numpy as np
+    a = torch.from_numpy(np.asarray(img)).float().permute(2, 0, 1) / 255.0
+    return torch.nn.functional.adaptive_avg_pool2d(a[None], 16)[0]
+
+
+def main():
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    for name, (sd, vb, kw) in CASES.items():
+        unet, vae, txt, proj = components(sd)
+        o = build_reference(unet, vae, DDIMRestated(), txt, sd_version=sd, view_batch_size=vb, projection_dim=proj)
+        o.seed_everything(SEED)
+        args = dict(DEFAULTS)
+        args.update(kw)
+        imgs, _, latent = run_reference(o, progress=lambda it: it, **args)
+        torch.save(dict(sd_version=sd, view_batch_size=vb, seed=SEED, kwargs=args, latent=latent.clone(),
+                        image_stats=torch.stack([image_stats(i) for i in imgs]), image_size=imgs[0].size),
+                   os.path.join(out_dir, name + ".pt"))
+        print(f"{name}: latent {tuple(latent.shape)} std {latent.std():.4f} images {len(imgs)} x {imgs[0].size}")
+
+
+if __name__ == "__main__":
+    main()

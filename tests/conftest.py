@@ -1,0 +1,67 @@
+import glob
+import importlib
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+PKG = importlib.import_module("elasticdiffusion-official_b200")
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA (sm_100) device; run with `-m gpu` on the B200 box")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
+def golden_names():
+    return sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.pt")))
+
+
+def load_golden(name):
+    return torch.load(os.path.join(GOLDEN_DIR, name + ".pt"), map_location="cpu", weights_only=False)
+
+
+def components(sd, device="cpu"):
+    """Same synthetic modules as scripts/make_golden.py (fixed-seed weights)."""
+    syn = PKG.synthetic
+    xl = sd.startswith("XL")
+    unet = syn.StubUNet(sample_size=128 if xl else 64, cross_dim=16, xl=xl, pooled_dim=8).to(device)
+    vae = syn.StubVAE().to(device)
+    txt = syn.StubTextEncoder(16, 8 if xl else None, device=device)
+    return unet, vae, txt, (8 if xl else None)
+
+
+def make_ed(sd, vb, device="cpu"):
+    unet, vae, txt, proj = components(sd, device)
+    return PKG.ElasticDiffusion.from_components(device, unet, vae, None, txt, sd_version=sd, view_batch_size=vb,
+                                                projection_dim=proj)
+
+
+def oracle_models(sd, vb, device="cpu"):
+    from oracle import reference_port as rp
+    from oracle.ddim_restated import DDIMRestated
+    unet, vae, txt, proj = components(sd, device)
+    return rp.Models(unet, vae, DDIMRestated(), txt, sd, device, vb, projection_dim=proj)
+
+
+def oracle_kwargs(kw):
+    """generate_image kwargs of a golden -> positional meaning for oracle.reference_port.denoise."""
+    return dict(prompts=kw["prompts"], negative_prompts=kw["negative_prompts"], height=kw["height"], width=kw["width"],
+                num_inference_steps=kw["num_inference_steps"], guidance_scale=kw["guidance_scale"],
+                resampling_steps=kw["resampling_steps"], new_p=kw["new_p"], rrg_stop_t=kw["rrg_stop_t"],
+                rrg_init_weight=kw["rrg_init_weight"], cosine_scale=kw["cosine_scale"],
+                repaint_sampling=kw["repaint_sampling"])

@@ -1,0 +1,175 @@
+"""CPU: the product's host-side logic (geometry tables, RNG ledger, DDIM scalars, C-ABI surface) against the oracle
+and the goldens.  No CUDA compute is called here."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import PKG, ROOT, golden_names, load_golden, make_ed, oracle_kwargs, oracle_models
+from oracle import reference_port as rp
+from oracle import wave_spec as ws
+
+geometry, native = PKG.geometry, PKG.native
+
+
+# ---- C ABI --------------------------------------------------------------------------------------------------------
+def test_library_loads_and_exports_every_declared_symbol():
+    native.build()
+    hdr = open(os.path.join(ROOT, "include", "elastic_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|const char\*)\s+(ed_\w+)\s*\(", hdr, flags=re.M))
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(native.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/elastic_b200.h but not exported"
+    assert declared == set(native.EXPORTS), "ctypes binding and header disagree"
+    L = native.lib()
+    assert L.ed_abi_version() == 1
+    assert L.ed_strerror(-2).decode().startswith("unsupported")
+
+
+def test_struct_layouts_match_header_sizes():
+    # ed_plan_t: 18 int32 + 15 pointers ; ed_step_params_t: 7 float + 5 int32 + 128 float ; ed_tiles_t: 10 int32 + 5 ptr
+    assert ctypes.sizeof(native.Plan) == 18 * 4 + 15 * 8
+    assert ctypes.sizeof(native.StepParams) == (7 + 5 + 128) * 4
+    assert ctypes.sizeof(native.Tiles) == 10 * 4 + 5 * 8
+
+
+def test_product_refuses_cpu_device_loudly():
+    ed = make_ed("2.1", 1)
+    with pytest.raises(native.NativeError):
+        ed.generate_image("a cat", height=512, width=512, num_inference_steps=1, resampling_steps=0,
+                          progress=lambda it: it)
+
+
+def test_constructor_without_diffusers_says_so():
+    with pytest.raises(ImportError, match="from_components"):
+        PKG.ElasticDiffusion(torch.device("cpu"), "2.1")
+
+
+def test_signatures_match_reference():
+    import inspect
+    sig = inspect.signature(PKG.ElasticDiffusion.generate_image)
+    assert list(sig.parameters)[1:] == ["prompts", "negative_prompts", "height", "width", "num_inference_steps",
+                                        "guidance_scale", "resampling_steps", "new_p", "rrg_stop_t", "rrg_init_weight",
+                                        "rrg_scherduler_cls", "cosine_scale", "repaint_sampling", "progress",
+                                        "tiled_decoder", "grid"]
+    d = {k: v.default for k, v in sig.parameters.items()}
+    assert (d["height"], d["width"], d["num_inference_steps"], d["guidance_scale"], d["resampling_steps"], d["new_p"],
+            d["rrg_stop_t"], d["rrg_init_weight"], d["cosine_scale"], d["repaint_sampling"], d["tiled_decoder"],
+            d["grid"]) == (768, 768, 50, 10.0, 20, 0.3, 0.2, 1000, 3.0, True, False, False)
+    assert d["rrg_scherduler_cls"] is PKG.CosineScheduler
+    init = inspect.signature(PKG.ElasticDiffusion.__init__)
+    assert list(init.parameters)[1:] == ["device", "sd_version", "verbose", "log_freq", "view_batch_size", "low_vram"]
+
+
+# ---- geometry vs oracle ---------------------------------------------------------------------------------------------
+SHAPES = [(64, 128, (32, 64), 64, 32), (128, 256, (64, 128), 128, 64), (192, 192, (128, 128), 128, 64),
+          (135, 240, (72, 128), 128, 64), (64, 64, (64, 64), 64, 32), (80, 112, (45, 64), 64, 32),
+          (256, 256, (128, 128), 128, 64), (96, 128, (48, 64), 64, 32), (128, 256, (64, 128), 128, 32)]
+
+
+@pytest.mark.parametrize("H,W,ds,native_sz,window", SHAPES)
+def test_geometry_tables_match_oracle(H, W, ds, native_sz, window):
+    geo = geometry.build_geometry(1, 4, H, W, native_sz, ds, window, window, native_sz - window)
+    tabs = rp.ResampleTables(H, W, ds)
+    assert geo.tables["row_src"] == tabs.row_src.tolist() and geo.tables["col_src"] == tabs.col_src.tolist()
+    assert (geo.lh, geo.lw) == (tabs.lh, tabs.lw)
+    for lo, n, groups in ((geo.tables["mrow_lo"], geo.tables["mrow_n"], tabs.row_groups),
+                          (geo.tables["mcol_lo"], geo.tables["mcol_n"], tabs.col_groups)):
+        for y, g in enumerate(groups):
+            assert tuple(range(lo[y], lo[y] + n[y])) == g
+        assert all(v == 0 for v in n[len(groups):])
+    # views / context boxes
+    h_ws = H if window + (native_sz - window) >= H else window
+    w_ws = W if window + (native_sz - window) >= W else window
+    views = rp.view_grid(H * 8, W * 8, h_ws, w_ws, window, 8)
+    assert geo.views == views and geo.nvr * geo.nvc == len(views)
+    n = (native_sz - window) // 2
+    for v, view in enumerate(views):
+        (r0, r1, c0, c1), (n_t, n_b, n_l, n_r) = rp.context_box(view, n, H, W)
+        assert geo.tables["views"][v * 8:v * 8 + 8] == [*view, r0, c0, n_t, n_l]
+        assert (r1 - r0, c1 - c0) == (geo.vh, geo.vw)
+    # covering ranges
+    for y in range(H):
+        cov = [r for r in range(geo.nvr) if views[r * geo.nvc][0] <= y < views[r * geo.nvc][1]]
+        assert cov == list(range(geo.tables["vrow_first"][y], geo.tables["vrow_first"][y] + geo.tables["vrow_cnt"][y]))
+    # nearest maps equal F.interpolate
+    x = torch.arange(geo.lh * geo.lw, dtype=torch.float32).view(1, 1, geo.lh, geo.lw)
+    up = torch.nn.functional.interpolate(x, size=(H, W), mode="nearest")
+    ur, uc = torch.tensor(geo.tables["up_row"]), torch.tensor(geo.tables["up_col"])
+    assert torch.equal(up[0, 0], x[0, 0][ur][:, uc])
+    y = torch.arange(H * W, dtype=torch.float32).view(1, 1, H, W)
+    dn = torch.nn.functional.interpolate(y, size=(geo.lh, geo.lw), mode="nearest")
+    dr, dc = torch.tensor(geo.tables["down_row"]), torch.tensor(geo.tables["down_col"])
+    assert torch.equal(dn[0, 0], y[0, 0][dr][:, dc])
+
+
+def test_geometry_rejects_what_the_reference_cannot_broadcast():
+    with pytest.raises(ValueError):
+        geometry.build_geometry(1, 4, 96, 160, 128, (76, 128), 64, 64, 64)   # XL 768x1280: reference fails at ed:637
+
+
+def test_low_res_size_and_tiles():
+    assert geometry.low_res_size(1024, 2048, "XL1.0", 8) == (64, 128)
+    assert geometry.low_res_size(512, 512, "1.5", 8) == (64, 64)
+    assert geometry.low_res_size(1080, 1920, "XL1.0", 8) == rp.downsample_size(1080, 1920, "XL1.0")
+    tg = geometry.build_tiles(256, 256, 128, 8)
+    assert (tg.core, tg.pad, tg.ntr, tg.ntc, len(tg.tiles)) == (32, 48, 8, 8, 64)
+    assert tg.tiles == rp.view_grid(2048, 2048, 32, 32, 32, 8)
+    tg = geometry.build_tiles(135, 240, 128, 8, low_vram=True)
+    assert tg.tiles == rp.view_grid(1080, 1920, 32, 32, 16, 8) and tg.pad == 32
+
+
+def test_ddim_scalars_match_oracle_step():
+    from oracle.ddim_restated import DDIMRestated
+    ddim = PKG.DDIMSchedule()
+    ref = DDIMRestated()
+    assert torch.equal(ddim.betas, ref.betas) and torch.equal(ddim.alphas_cumprod, ref.alphas_cumprod)
+    ddim.set_timesteps(7)
+    ref.set_timesteps(7)
+    assert torch.equal(ddim.timesteps, ref.timesteps)
+    mod = __import__("importlib").import_module(PKG.__name__ + ".ddim")
+    x, e = torch.randn(1, 4, 8, 8), torch.randn(1, 4, 8, 8)
+    for t in ddim.timesteps:
+        sc = mod.step_scalars(ddim, t)
+        f = lambda v: torch.tensor(v, dtype=torch.float32)
+        x0 = (x - f(sc["sqrt_beta_t"]) * e) / f(sc["sqrt_alpha_t"])
+        prev = f(sc["sqrt_alpha_prev"]) * x0 + f(sc["sqrt_dir"]) * e
+        out = ref.step(e, t, x)
+        assert torch.equal(x0, out["pred_original_sample"]) and torch.equal(prev, out["prev_sample"])
+
+
+# ---- RNG ledger vs oracle trace ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["sd21_512x1024_T4_R4", "sd15_512x512_T5_R3", "xl_1080x1920_T2_R2"])
+def test_ledger_replays_the_reference_pick_indices(name):
+    g = load_golden(name)
+    kw = oracle_kwargs(g["kwargs"])
+    m = oracle_models(g["sd_version"], g["view_batch_size"])
+    rp.seed_all(g["seed"], "cpu")
+    trace = {}
+    rp.denoise(m, trace=trace, **kw)
+    ed = make_ed(g["sd_version"], g["view_batch_size"])
+    ed.seed_everything(g["seed"])
+    tr2 = {}
+    ws.denoise_wave_form(ed, trace=tr2, **kw)
+    R1 = kw["resampling_steps"] + 1
+    ref_idx = trace["idx"]                       # one entry per resampling iteration of every wave-1 call
+    assert len(ref_idx) == len(tr2["idx"]) * R1
+    for s, tab in enumerate(tr2["idx"]):
+        for k in range(R1):
+            assert torch.equal(tab[k].long(), ref_idx[s * R1 + k].cpu())
+
+
+# ---- whole wave-batched dataflow on CPU (spec kernels) vs goldens --------------------------------------------------
+@pytest.mark.parametrize("name", [n for n in golden_names() if "2048x2048" not in n])
+def test_wave_form_reproduces_goldens(name):
+    g = load_golden(name)
+    ed = make_ed(g["sd_version"], g["view_batch_size"])
+    ed.seed_everything(g["seed"])
+    lat = ws.denoise_wave_form(ed, **oracle_kwargs(g["kwargs"]))
+    err = (lat - g["latent"]).abs().max().item()
+    # one UNet call per wave instead of one per pass: conv batching may change the last bits on CPU
+    assert err <= 2e-5, f"max abs diff {err:.3e}"
+    assert torch.mean((lat - g["latent"]) ** 2).item() < 1e-9

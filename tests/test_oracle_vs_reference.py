@@ -1,0 +1,87 @@
+"""CPU, build container only: the oracle against the LIVE unmodified reference (skipped where /root/reference is
+absent, e.g. on the GPU box - there the committed goldens stand in)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import components
+from oracle import reference_port as rp
+from oracle.ddim_restated import DDIMRestated
+from oracle.ref_shim import build_reference, reference_available, run_reference
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason="reference sources not present")
+
+
+def _ref(sd, vb):
+    unet, vae, txt, proj = components(sd)
+    return build_reference(unet, vae, DDIMRestated(), txt, sd_version=sd, view_batch_size=vb, projection_dim=proj)
+
+
+@pytest.mark.parametrize("H,W,ws,stride", [(512, 512, 32, 32), (1024, 2048, 64, 64), (1080, 1920, 64, 64),
+                                            (768, 1024, 32, 32), (2048, 2048, 32, 16), (640, 896, 48, 48)])
+def test_view_grid(H, W, ws, stride):
+    o = _ref("2.1", 1)
+    assert rp.view_grid(H, W, ws, ws, stride, 8) == o.get_views(H, W, h_ws=ws, w_ws=ws, stride=stride)
+
+
+@pytest.mark.parametrize("H,W", [(64, 128), (135, 240), (96, 128), (256, 256), (80, 112)])
+def test_context_box_equals_crop_with_context(H, W):
+    o = _ref("XL1.0", 1)
+    X = torch.randn(1, 4, H, W)
+    for ws, n in [(64, 32), (32, 16), (48, 8)]:
+        for v in rp.view_grid(H * 8, W * 8, min(ws, H), min(ws, W), ws, 8):
+            crop, ctx = o.crop_with_context(X, *v, S=1, n=n)
+            (r0, r1, c0, c1), ctx2 = rp.context_box(v, n, H, W)
+            assert tuple(ctx) == tuple(ctx2)
+            assert torch.equal(crop, X[:, :, r0:r1, c0:c1])
+
+
+@pytest.mark.parametrize("H,W,ds", [(128, 256, (64, 128)), (192, 192, (128, 128)), (135, 240, (72, 128)),
+                                     (64, 64, (64, 64)), (80, 112, (45, 64)), (96, 128, (48, 64))])
+def test_pick_and_mask_equals_random_nearest_downsample(H, W, ds):
+    o = _ref("2.1", 1)
+    o.random_downasmple_pre = {}
+    X = torch.randn(1, 4, H, W)
+    torch.manual_seed(3)
+    tabs = rp.ResampleTables(H, W, ds)
+    # nearest (top-left) pass
+    low, mask, idx = o.random_nearest_downsample(X, ds, nearest=True)
+    low2, mask2 = rp.pick_and_mask(X, tabs, torch.zeros(tabs.lh * tabs.lw, dtype=torch.long))
+    assert torch.equal(low, low2) and torch.equal(mask, mask2[:mask.shape[0], :mask.shape[1]])
+    # random pass with an exclude mask and previous indices: same RNG stream on both sides
+    excl = torch.zeros(len(idx), 4, dtype=torch.bool)
+    excl[torch.arange(len(idx)), idx] = True
+    torch.manual_seed(11)
+    low, mask, idx_r = o.random_nearest_downsample(X, ds, prev_random_indices=idx, exclude_mask=excl, drop_p=0.7)
+    torch.manual_seed(11)
+    idx_m = rp.mix_with_previous(rp.draw_cell_indices(len(idx), excl), idx, 0.7, "cpu")
+    assert torch.equal(idx_r, idx_m)
+    low2, mask2 = rp.pick_and_mask(X, tabs, idx_m)
+    assert torch.equal(low, low2) and torch.equal(mask, mask2[:mask.shape[0], :mask.shape[1]])
+
+
+def test_rrg_closed_form_vs_reference_autograd():
+    o = _ref("2.1", 1)
+    o.scheduler.set_timesteps(10)
+    t = o.scheduler.timesteps[2]
+    x0 = torch.randn(2, 4, 64, 128)
+    lat, un, di = torch.randn(2, 4, 32, 64), torch.randn(2, 4, 32, 64), torch.randn(2, 4, 32, 64)
+    g, _ = o.reduced_resolution_guidance(x0, t, None, x0, None, None, None, guidance_scale=3.3, rrg_scale=np.float64(417.3),
+                                         downsample_size=(32, 64),
+                                         donwsampled_scores={"latent": lat, "uncond_score": un, "direction": di})
+    m = rp.Models(o.unet, o.vae, o.scheduler, None, "2.1")
+    g2, _ = rp.rrg_gradient(m, t, x0, lat, un, di, 3.3, np.float64(417.3))
+    assert torch.equal(g, g2)
+
+
+@pytest.mark.parametrize("sd,H,W,T,R,vb", [("2.1", 512, 768, 2, 2, 3), ("XL1.0", 1024, 1536, 2, 1, 2)])
+def test_end_to_end_live(sd, H, W, T, R, vb):
+    o = _ref(sd, vb)
+    o.seed_everything(5)
+    _, _, lat = run_reference(o, prompts="a", negative_prompts="b", height=H, width=W, num_inference_steps=T,
+                              resampling_steps=R, progress=lambda it: it)
+    unet, vae, txt, proj = components(sd)
+    m = rp.Models(unet, vae, DDIMRestated(), txt, sd, "cpu", vb, projection_dim=proj)
+    rp.seed_all(5, "cpu")
+    mine = rp.denoise(m, "a", "b", H, W, T, resampling_steps=R)
+    assert torch.equal(mine, lat)
