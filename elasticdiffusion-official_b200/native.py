@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libelastic_b200.so")
 SOURCES = ["abi.cu", "gather.cu", "epilogue.cu", "tiles.cu"]
-ED_MAX_RENOISE = 64
+ED_MAX_RENOISE = 1000
 ED_F32, ED_F16, ED_BF16 = 0, 1, 2
 FLAG_RENOISE, FLAG_RRG, FLAG_FP16_SEM = 1, 2, 4
 

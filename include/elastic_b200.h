@@ -28,7 +28,7 @@ extern "C" {
 #endif
 
 #define ED_ABI_VERSION 1
-#define ED_MAX_RENOISE 64
+#define ED_MAX_RENOISE 1000
 
 typedef enum {
   ED_OK = 0,

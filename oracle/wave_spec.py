@@ -125,8 +125,10 @@ def _local_uncond_full(geo, R1, unet_out):
 def spec_epilogue(geo, prm, latent, unet_out, idx, noise=None):
     """ed_wave_epilogue.  `prm`: dict with the ed_step_params_t fields (flags as an int).
     Returns (out_latent, x0)."""
-    f32 = lambda v: torch.tensor(v, dtype=torch.float32)
     dev = latent.device
+    # 0-dim tensors ON the data's device: torch's CUDA division by a *CPU* scalar multiplies by the reciprocal instead
+    # of dividing (1 ulp off the CPU result); a device operand takes the IEEE division kernel on every backend.
+    f32 = lambda v: torch.tensor(v, dtype=torch.float32, device=dev)
     R1, flags = prm["R1"], prm["flags"]
     fp16sem = bool(flags & 4)
     g, sb, sa = f32(prm["guidance"]), f32(prm["sqrt_beta_t"]), f32(prm["sqrt_alpha_t"])

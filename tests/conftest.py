@@ -14,6 +14,11 @@ PKG = importlib.import_module("elasticdiffusion-official_b200")
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
 
+# fp32 parity runs: no TF32 in cuDNN / cuBLAS (the stand-in UNet's convs would otherwise differ from CPU fp32 by ~1e-3)
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA (sm_100) device; run with `-m gpu` on the B200 box")
 
