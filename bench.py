@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""bench.py - denoise-steps/sec of the ElasticDiffusion global/local patched denoising loop (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg3|cfg2|cfg4]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one denoise step of `generate_image` (reference elastic_diffusion.py:1013-1078): 2 waves (resampling
+global passes + local views, repaint re-noising, second estimate, RRG) on synthetic data of the BASELINE shape.
+Workload cfg3 = SDXL 1024x2048, view_batch_size=16, 50 steps, resampling_steps=7, rrg=1000 (BASELINE.json configs[2],
+the configuration the metric is quoted on).  No diffusers / weights exist offline, so the UNet is `StandInUNet("XL1.0")`
+(SDXL-base stage widths and transformer depths, random weights), the VAE / text encoder are small stand-ins
+(`data: synthetic`).  The same module definitions feed the reference arm.
+
+Own arm (default): CUDA kernels through libelastic_b200's C ABI + PyTorch UNet; prints ONE JSON line with
+`roofline`, `cpu_baseline`, `e2e`, `gpu_launches`, `clocks`.
+Reference arm (`--impl reference`): the reference algorithm's CPU path (oracle port - the reference itself is Python
+and cannot travel to the GPU box) on the host cores, bounded sample, same metric / config.
+"""
+import argparse
+import ctypes
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (sd_version, unet preset, height, width, view_batch_size, T, R, cross_dim, pooled_dim)
+    "cfg3": ("XL1.0", "XL1.0", 1024, 2048, 16, 50, 7, 2048, 1280),
+    "cfg4": ("XL1.0", "XL1.0", 2048, 2048, 16, 50, 7, 2048, 1280),
+    "cfg2": ("2.1", "2.1", 512, 1024, 8, 50, 4, 1024, None),
+    "tiny": ("XL1.0", "tiny-xl", 1024, 2048, 16, 50, 7, 64, 32),     # quick functional run of the same topology
+}
+GEN = dict(prompts="a photo of a mountain lake at sunrise", negative_prompts="blurry, ugly", guidance_scale=10.0,
+           new_p=0.3, rrg_stop_t=0.2, rrg_init_weight=1000, cosine_scale=10.0, repaint_sampling=True)
+
+
+def pkg():
+    return importlib.import_module("elasticdiffusion-official_b200")
+
+
+def build_modules(workload, device, unet_dtype):
+    sd, preset, H, W, vb, T, R, cross, pooled = WORKLOADS[workload]
+    syn = pkg().synthetic
+    unet = syn.StandInUNet(preset, device=device, dtype=unet_dtype).eval()
+    for p in unet.parameters():
+        p.requires_grad_(False)
+    vae = syn.StubVAE().to(device)
+    txt = syn.StubTextEncoder(cross, pooled, device=device)
+    return unet, vae, txt
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# L2-exceeding kernel roofline (live, CUDA events on the launching stream)
+# ---------------------------------------------------------------------------------------------------------------
+def kernel_rooflines(device, B=96, out_dtype=torch.bfloat16, iters=10, warm=3):
+    """Times every hot-path kernel of libelastic_b200 on a batch of B SDXL 1024x2048 latents (working sets of
+    0.1-1.3 GiB, all larger than the 126 MB L2) and returns algorithmic GB/s per kernel."""
+    P = pkg()
+    native, geometry = P.native, P.geometry
+    L = native.lib()
+    C, H, W, nat, R1, n_re = 4, 128, 256, 128, 8, 20
+    geo = geometry.build_geometry(B, C, H, W, nat, (64, 128), 64, 64, 64)
+    keep = {k: torch.tensor(v if len(v) else [0], dtype=torch.int32, device=device) for k, v in geo.tables.items()}
+    lp, rp, tp, bp = geo.g_pad
+    plan = native.Plan(B=B, C=C, H=H, W=W, dH=nat, dW=nat, lh=geo.lh, lw=geo.lw, g_tp=tp, g_lp=lp, nv=geo.nv,
+                       nvr=geo.nvr, nvc=geo.nvc, vh=geo.vh, vw=geo.vw, v_tp=0, v_lp=0,
+                       **{k: v.data_ptr() for k, v in keep.items()})
+    st = native.stream_handle()
+    x = torch.randn(B, C, H, W, device=device)
+    y = torch.empty_like(x)
+    idx = torch.randint(0, 4, (R1, geo.lh * geo.lw), device=device, dtype=torch.uint8)
+    idx[0] = 0
+    strips = [None, None, torch.randn(1, C, tp, nat, device=device), torch.randn(1, C, bp, nat, device=device)]
+    n = 2 * B * R1 + geo.nv * B
+    so = torch.empty(0, dtype=out_dtype).element_size()
+    canvas32 = torch.empty(geo.nv * B, C, nat, nat, device=device)
+    canvas = torch.empty(n, C, nat, nat, device=device, dtype=out_dtype)
+    out = torch.randn(n, C, nat, nat, device=device, dtype=torch.float32).to(out_dtype)
+    noise = torch.randn(n_re, B, C, H, W, device=device)
+    sp = native.StepParams(guidance=10.0, sqrt_beta_t=0.96, sqrt_alpha_t=0.27, sqrt_alpha_prev=0.33, sqrt_dir=0.94,
+                           rrg_weight=700.0, rrg_norm=2.0 / (C * H * W), flags=1, n_renoise=n_re, R1=R1)
+    for k in range(n_re):
+        sp.renoise_a[k], sp.renoise_b[k] = 0.995, 0.1
+    d_prm = torch.empty(2, ctypes.sizeof(native.StepParams), dtype=torch.uint8, device=device)
+    native.check(L.ed_upload_step_params(native.ptr(d_prm[0]), ctypes.byref(sp), st))
+    sp.flags = 2
+    native.check(L.ed_upload_step_params(native.ptr(d_prm[1]), ctypes.byref(sp), st))
+    owner = torch.empty(H * W, dtype=torch.uint8, device=device)
+    native.check(L.ed_owner_map(ctypes.byref(plan), R1, native.ptr(idx), native.ptr(owner), st))
+    Lb = B * C * H * W * 4
+    low = B * C * geo.lh * geo.lw
+    win = geo.nv * B * C * 128 * 64          # windows tile the latent exactly at this shape
+    cases = {
+        "ed_gather_views(tma)": (
+            lambda: L.ed_gather_views(ctypes.byref(plan), native.ptr(x), native.ptr(canvas32), native.ED_F32, 0, st),
+            2 * geo.nv * B * C * geo.vh * geo.vw * 4),
+        "ed_random_pick_gather": (
+            lambda: L.ed_random_pick_gather(ctypes.byref(plan), R1, native.ptr(x), native.ptr(idx),
+                                            native.strips_array(strips), native.ptr(canvas), native.dtype_code(out_dtype), st),
+            R1 * (low * 4 + geo.lh * geo.lw + 2 * B * C * nat * nat * so)),
+        "ed_wave_epilogue+renoise": (
+            lambda: L.ed_wave_epilogue(ctypes.byref(plan), native.ptr(d_prm[0]), native.ptr(x), native.ptr(out),
+                                       native.dtype_code(out_dtype), native.ptr(idx), native.ptr(owner), native.ptr(noise),
+                                       native.ptr(y), None, st),
+            Lb + win * so + 2 * low * so + R1 * geo.lh * geo.lw + n_re * Lb + Lb),
+        "ed_wave_epilogue+rrg": (
+            lambda: L.ed_wave_epilogue(ctypes.byref(plan), native.ptr(d_prm[1]), native.ptr(x), native.ptr(out),
+                                       native.dtype_code(out_dtype), native.ptr(idx), native.ptr(owner), None, native.ptr(y), None, st),
+            Lb + win * so + 2 * low * so + R1 * geo.lh * geo.lw + low * 4 + low * so + Lb),
+        "ed_renoise": (
+            lambda: L.ed_renoise(native.ptr(d_prm[0]), native.ptr(x), native.ptr(noise), native.ptr(y), x.numel(), st),
+            (2 + n_re) * Lb),
+    }
+    # tiled-decode blend at cfg4's shape: 64 tiles x (3,1024,1024) decoded patches -> (3,2048,2048), batch 4
+    tg = geometry.build_tiles(256, 256, 128, 8)
+    tb = 4
+    tabs = {k: torch.tensor(v, dtype=torch.int32, device=device) for k, v in tg.tables.items()}
+    T = tg.core + 2 * tg.pad
+    patches = torch.randn(len(tg.tiles) * tb, 3, T * 8, T * 8, device=device, dtype=out_dtype)
+    image = torch.empty(tb, 3, 2048, 2048, device=device)
+    tt = native.Tiles(ntiles=len(tg.tiles), ntc=tg.ntc, core=tg.core, pad=tg.pad, scale=8, B=tb, CH=3, H=256, W=256,
+                      tiles=tabs["tiles"].data_ptr(), trow_first=tabs["trow_first"].data_ptr(),
+                      trow_cnt=tabs["trow_cnt"].data_ptr(), tcol_first=tabs["tcol_first"].data_ptr(),
+                      tcol_cnt=tabs["tcol_cnt"].data_ptr())
+    cases["ed_tile_blend"] = (
+        lambda: L.ed_tile_blend(ctypes.byref(tt), native.ptr(patches), native.dtype_code(out_dtype), native.ptr(image), st),
+        len(tg.tiles) * tb * 3 * (8 * tg.core) ** 2 * so + tb * 3 * 2048 * 2048 * 4)
+    zl = torch.randn(tb * 16, 4, 256, 256, device=device)
+    boxes = torch.empty(len(tg.tiles) * tb * 16, 4, T, T, device=device)
+    cases["ed_tile_gather(tma)"] = (
+        lambda: L.ed_tile_gather(native.ptr(zl), tb * 16, 4, 256, 256, native.ptr(tabs["tiles"]), len(tg.tiles), tg.core,
+                                 tg.pad, native.ptr(boxes), st),
+        zl.numel() * 4 + boxes.numel() * 4)      # every latent element read at least once + all boxes written
+    peak, how = peaks()
+    res = {}
+    for name, (fn, nbytes) in cases.items():
+        for _ in range(warm):
+            native.check(fn(), name)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            native.check(fn(), name)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        gbs = nbytes / ms / 1e6
+        res[name] = {"ms": round(ms, 4), "algorithmic_MB": round(nbytes / 1e6, 1), "GB/s": round(gbs, 1),
+                     "frac": round(gbs / peak, 3)}
+    return res, peak, how
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_reference_sample(workload, threads=None):
+    """Reference CPU path (oracle port = restated reference, fp32) on a bounded sample of one denoise step.
+
+    One full step at cfg3 is 9 batch-2 + 2 batch-4 SDXL-sized UNet calls in fp32 - minutes on host cores - so the
+    sample is: ONE batch-2 UNet call of the stand-in (timed), and one full step of the loop with the tiny StubUNet
+    (glue: resampling, gathers, scatters, DDIM, undo, RRG + 18 VAE-stub encodes).  steps/s = 1 / (13 * t_b2 + glue)
+    (26 sample-forwards per step = 13 batch-2 equivalents)."""
+    from oracle import reference_port as rp
+    from oracle.ddim_restated import DDIMRestated
+    sd, preset, H, W, vb, T, R, cross, pooled = WORKLOADS[workload]
+    if threads:
+        torch.set_num_threads(threads)
+    cores = torch.get_num_threads()
+    syn = pkg().synthetic
+    xl = sd.startswith("XL")
+    with torch.no_grad():
+        stub = syn.StubUNet(sample_size=128 if xl else 64, cross_dim=16, xl=xl, pooled_dim=8)
+        m = rp.Models(stub, syn.StubVAE(), DDIMRestated(), syn.StubTextEncoder(16, 8 if xl else None), sd, "cpu", vb,
+                      projection_dim=8 if xl else None)
+        rp.seed_all(0, "cpu")
+        kw = dict(GEN, height=H, width=W, num_inference_steps=T, resampling_steps=R)
+        kw.pop("prompts_unused", None)
+        marks = []
+        class Stop(Exception):
+            pass
+        def cb(i, x, x0):
+            marks.append(time.perf_counter())
+            if len(marks) == 3:
+                raise Stop
+        t_start = time.perf_counter()
+        try:
+            rp.denoise(m, step_callback=cb, **kw)
+        except Stop:
+            pass
+        glue = (marks[2] - marks[0]) / 2          # steps 2 and 3 (step 1 warms caches)
+        unet = syn.StandInUNet(preset).eval()
+        nat = 128 if xl else 64
+        x = torch.randn(2, 4, nat, nat)
+        ehs = torch.randn(2, 77, cross)
+        kwu = {}
+        if pooled is not None:
+            kwu["added_cond_kwargs"] = {"text_embeds": torch.randn(2, pooled),
+                                        "time_ids": torch.tensor([[4 * H, 4 * W, 0, 0, 4 * H, 4 * W]] * 2, dtype=torch.float32)}
+        t0 = time.perf_counter()
+        unet(x, torch.tensor(981), encoder_hidden_states=ehs, **kwu)
+        t_b2 = time.perf_counter() - t0
+    n_samples = {"cfg3": 26, "cfg2": 20, "cfg4": 50, "tiny": 26}[workload]
+    step_s = (n_samples / 2) * t_b2 + glue
+    return {"value": 1.0 / step_s, "unit": "denoise-steps/s", "cores": cores, "kind": "port",
+            "sample": f"1 batch-2 {preset} stand-in UNet forward on CPU fp32 ({t_b2:.2f} s) x {n_samples // 2} + one step of "
+                      f"glue with the stub UNet/VAE ({glue * 1e3:.0f} ms); extrapolated to one full step "
+                      f"({step_s:.2f} s)", "t_unet_b2_s": t_b2, "glue_s": glue}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = cpu_reference_sample(args.workload)
+    sd, preset, H, W, vb, T, R, cross, pooled = WORKLOADS[args.workload]
+    line = {"impl": "reference", "metric": "denoise-steps/sec", "value": res["value"], "unit": "denoise-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / res["value"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.workload, args.gpus), "cpu_baseline": res,
+            "e2e": {"value": res["value"], "unit": "denoise-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(workload, n):
+    sd, preset, H, W, vb, T, R, cross, pooled = WORKLOADS[workload]
+    return {"workload": f"{workload}: SD{sd} {H}x{W} view_batch_size={vb} steps={T} resampling_steps={R} rrg=1000 "
+                        "cosine_scale=10 repaint", "unet": f"StandInUNet({preset}) random weights",
+            "parallelism": f"wave-sample sharding x{n}" if n > 1 else "single GPU",
+            "timing": "CUDA events; latent working set < L2, UNet activations/weights (5 GB bf16) >> L2"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=list(WORKLOADS))
+    ap.add_argument("--no-extras", action="store_true", help="skip roofline / cpu_baseline / e2e legs (debug)")
+    ap.add_argument("--roofline-only", action="store_true", help="only the L2-exceeding kernel roofline table (debug / ncu)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    if args.roofline_only:
+        torch.cuda.set_device(0)
+        roof, peak, how = kernel_rooflines(torch.device("cuda", 0))
+        print(json.dumps({"roofline_all": roof, "peak": peak, "peak_source": how}))
+        return
+
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    W_, K = max(args.warmup, 3), args.steps
+    sd, preset, H, Wd, vb, T, R, cross, pooled = WORKLOADS[args.workload]
+    P = pkg()
+    unet_dtype = torch.bfloat16
+    unet, vae, txt = build_modules(args.workload, device, unet_dtype)
+    ed = P.ElasticDiffusion.from_components(device, unet, vae, None, txt, sd_version=sd, view_batch_size=vb,
+                                            projection_dim=pooled)
+    ed.autocast = False                 # UNet weights are bf16 already: no per-call weight re-casting
+    ed.unet_input_dtype = unet_dtype    # gather kernels write the UNet batch directly in bf16
+    ed.use_cuda_graphs = os.environ.get("BENCH_GRAPHS", "1") == "1"   # each wave's UNet forward replayed as a CUDA graph
+    if os.environ.get("BENCH_CL", "0") == "1":
+        unet.to(memory_format=torch.channels_last)
+    kw = dict(GEN, height=H, width=Wd, num_inference_steps=T, resampling_steps=R, progress=lambda it: it)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_run(host_io):
+        """W_ warm-up steps then exactly K timed steps of the denoise loop; returns (seconds, launches, byte counts)."""
+        ev = {}
+        state = {"launch0": 0, "d2h": 0}
+        host_lat = torch.empty(1, 4, H // 8, Wd // 8, pin_memory=True) if host_io else None
+
+        def cb(i, x):
+            if host_io:                                    # the step's result is read back to pinned host memory
+                host_lat.copy_(x)
+                state["d2h"] = host_lat.numel() * 4
+            if i == W_ - 1:
+                barrier()
+                state["launch0"] = ed.last_run["kernel_launches"]
+                ed.profile_kernels = not host_io
+                ed._kernel_events = {}
+                ev["t0"] = torch.cuda.Event(enable_timing=True)
+                ev["t0"].record()
+            if i == W_ + K - 1:
+                ev["t1"] = torch.cuda.Event(enable_timing=True)
+                ev["t1"].record()
+                barrier()
+                ed.profile_kernels = False
+        ed.seed_everything(0)
+        if host_io:
+            # inputs start in pinned HOST memory and are copied inside the call (text embeddings; the latent is drawn
+            # on the device by the API itself like the reference does, ed:998)
+            emb_fn = ed._text_embeds_fn
+            host = [tuple(z.cpu().pin_memory() for z in emb_fn(p)) for p in ([kw["negative_prompts"]], [kw["prompts"]])]
+            it = iter(host)
+            ed._text_embeds_fn = lambda prompts: tuple(z.to(device, non_blocking=True) for z in next(it))
+        try:
+            ed.denoise(step_callback=cb, max_steps=W_ + K, **kw)
+        finally:
+            if host_io:
+                ed._text_embeds_fn = emb_fn
+        sec = ev["t0"].elapsed_time(ev["t1"]) / 1e3
+        t = torch.tensor([sec], device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), ed.last_run["kernel_launches"] - state["launch0"], state["d2h"]
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    sec, launches, _ = timed_run(host_io=False)
+    clk = clocks.stop() if rank == 0 else None
+    ktimes = ed.kernel_times_ms()
+    value = K / sec
+    line = {"metric": "denoise-steps/sec", "value": value, "unit": "denoise-steps/s", "n_gpus": world, "steps": K,
+            "warmup": W_, "ms_per_step": 1e3 * sec / K, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args.workload, world),
+            "gpu_launches": launches, "clocks": clk,
+            "unet": {"calls": ed.last_run["unet_calls"], "samples": ed.last_run["unet_samples"],
+                     "collectives": ed.last_run["collectives"]},
+            "kernels_in_step": {k: {"launches": n, "avg_us": round(1e3 * ms / max(n, 1), 2)} for k, (n, ms) in ktimes.items()}}
+    if not args.no_extras:
+        sec2, _, d2h = timed_run(host_io=True)
+        n_cells = (H // 16) * (Wd // 16)
+        h2d = (R + 1) * n_cells + 2 * ctypes.sizeof(P.native.StepParams) + 2 * 2 * (77 * cross + (pooled or 0)) * 4 // (W_ + K)
+        line["e2e"] = {"value": K / sec2, "unit": "denoise-steps/s", "h2d_bytes_per_step": int(h2d),
+                       "d2h_bytes_per_step": int(d2h + R * n_cells * 8),
+                       "note": "denoise() with text embeddings copied from pinned host memory, per-step plan tables / "
+                               "step params uploaded, drop-mask draws and the step's latent read back to the host"}
+        if rank == 0 or world == 1:
+            roof, peak, how = kernel_rooflines(device)
+            dom = "ed_wave_epilogue+renoise"
+            line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": roof[dom]["GB/s"], "peak": peak,
+                                "unit": "GB/s", "frac": roof[dom]["frac"], "traffic": None, "peak_source": how,
+                                "sizes": "B=96 SDXL 1024x2048 latents per launch (L2-exceeding); in-pipeline launches are "
+                                         "L2-resident and latency-bound, see kernels_in_step"}
+            line["roofline_all"] = roof
+        if rank == 0 and world == 1:
+            line["cpu_baseline"] = cpu_reference_sample(args.workload)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -31,6 +31,12 @@ template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; 
 template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
 template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
+// read-only (non-coherent) scalar load: lets the compiler hoist / batch loads across the kernel's stores
+template <typename T> __device__ __forceinline__ float ld_ro(const T* p);
+template <> __device__ __forceinline__ float ld_ro<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float ld_ro<__half>(const __half* p) { return __half2float(__ldg(p)); }
+template <> __device__ __forceinline__ float ld_ro<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(__ldg(p)); }
+
 template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }

@@ -11,6 +11,10 @@
 // that with identical UNet outputs the result is bit-identical to eager fp32 PyTorch on CPU.
 #include "common.cuh"
 
+#ifndef ED_EPI_MINB
+#define ED_EPI_MINB 2   // CTAs of 256 threads per SM the epilogue is compiled for (register cap 65536 / (256 * MINB))
+#endif
+
 namespace ed {
 
 struct EpiArgs {
@@ -19,175 +23,243 @@ struct EpiArgs {
   const float* latent;
   const void* unet_out;
   const uint8_t* idx;
+  const uint8_t* owner;
   const float* noise;
   float* out_latent;
   float* out_x0;
 };
 
 // Which resampling iteration wrote target_direction[y, x] last (ed:637: every iteration overwrites where its mask is
-// set; ed:643-644: what is still NaN after the last iteration takes the last iteration's value).
+// set; ed:643-644: what is still NaN after the last iteration takes the last iteration's value).  All idx bytes are
+// loaded unconditionally (independent loads, one memory round trip) and the owner is the highest k whose mask hits.
 __device__ __forceinline__ int owner_iteration(const ed_plan_t& P, const uint8_t* __restrict__ idx, int R1, int y, int x) {
   const int rlo = __ldg(P.mrow_lo + y), rn = __ldg(P.mrow_n + y);
   const int clo = __ldg(P.mcol_lo + x), cn = __ldg(P.mcol_n + x);
   const int cells = P.lh * P.lw;
-  for (int k = R1 - 1; k > 0; --k) {
-    const uint8_t* t = idx + (long long)k * cells;
-    for (int a = 0; a < rn; ++a) {
-      const int ry = rlo + a;
-      for (int e = 0; e < cn; ++e) {
-        const int rx = clo + e;
-        if (t[(ry >> 1) * P.lw + (rx >> 1)] == (((ry & 1) << 1) | (rx & 1))) return k;
-      }
+  int owner = -1;
+  if (rn == 1 && cn == 1) {   // exact 1/2 (or identity) ratio: one cell, one code
+    const int cell = (rlo >> 1) * P.lw + (clo >> 1);
+    const int code = ((rlo & 1) << 1) | (clo & 1);
+#pragma unroll 4
+    for (int k = 0; k < R1; ++k) owner = (__ldg(idx + k * cells + cell) == code) ? k : owner;
+  } else {
+    for (int k = 0; k < R1; ++k) {
+      const uint8_t* t = idx + k * cells;
+      bool hit = false;
+      for (int a = 0; a < rn; ++a)
+        for (int e = 0; e < cn; ++e) {
+          const int ry = rlo + a, rx = clo + e;
+          hit |= __ldg(t + (ry >> 1) * P.lw + (rx >> 1)) == (((ry & 1) << 1) | (rx & 1));
+        }
+      owner = hit ? k : owner;
     }
   }
-  // iteration 0 either owns the pixel through its own mask, or nothing does and the NaN back-fill of the last
-  // iteration applies.
-  if (R1 > 1) {
-    const uint8_t* t = idx;
-    bool hit = false;
-    for (int a = 0; a < rn; ++a)
-      for (int e = 0; e < cn; ++e) {
-        const int ry = rlo + a, rx = clo + e;
-        hit |= t[(ry >> 1) * P.lw + (rx >> 1)] == (((ry & 1) << 1) | (rx & 1));
-      }
-    return hit ? 0 : R1 - 1;
+  return owner < 0 ? R1 - 1 : owner;
+}
+
+// Per-pixel, channel-independent references.  Everything static comes from the host-built tables of the plan
+// (pix_ref / cell_cand / cell_down); the only per-wave inputs are the owner map and the last iteration's pick bytes.
+struct PixelRefs {
+  int dir_k, dir_off;     // owner iteration of target_direction here + offset of the low-res cell inside a canvas plane
+  int view, view_off;     // single covering view and the pixel's offset in its canvas plane; view = -1: several windows
+                          // cover the pixel (overlapping last row / column) -> table walk per channel
+  int lat_off;            // RRG: offset in a latent plane of the pixel the LAST iteration picked for that low-res cell
+  int ddir_k, ddir_off;   // RRG: owner + cell offset at the full-res pixel nearest-DOWNsampling reads for that cell
+};
+
+__device__ __forceinline__ void pixel_refs(const ed_plan_t& P, const uint8_t* __restrict__ idx,
+                                           const uint8_t* __restrict__ owner, int R1, int pix, bool rrg, PixelRefs& r) {
+  const int4 s = __ldg(reinterpret_cast<const int4*>(P.pix_ref) + pix);
+  r.dir_k = __ldg(owner + pix);
+  r.dir_off = s.x;
+  r.view = s.y;
+  r.view_off = s.z;
+  if (rrg) {
+    const int cell = s.w;
+    const int pick = __ldg(idx + (R1 - 1) * P.lh * P.lw + cell) & 3;
+    r.lat_off = __ldg(P.cell_cand + cell * 4 + pick);
+    const int2 d = __ldg(reinterpret_cast<const int2*>(P.cell_down) + cell);
+    r.ddir_k = __ldg(owner + d.x);
+    r.ddir_off = d.y;
   }
-  return 0;
+}
+
+__global__ void __launch_bounds__(256) owner_map_kernel(const ed_plan_t P, int R1, const uint8_t* __restrict__ idx,
+                                                        uint8_t* __restrict__ owner) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x < P.W && y < P.H) owner[y * P.W + x] = (uint8_t)owner_iteration(P, idx, R1, y, x);
 }
 
 template <typename OT>
-__device__ __forceinline__ float direction_at(const ed_plan_t& P, const OT* __restrict__ out, const uint8_t* idx, int R1,
-                                              int b, int c, int y, int x, bool fp16sem) {
-  const int k = owner_iteration(P, idx, R1, y, x);
-  const long long plane = (long long)P.dH * P.dW;
-  const long long off = (long long)(P.g_tp + __ldg(P.up_row + y)) * P.dW + P.g_lp + __ldg(P.up_col + x);
-  const float un = to_f32<OT>(out[(((long long)(k * 2 + 0) * P.B + b) * P.C + c) * plane + off]);
-  const float co = to_f32<OT>(out[(((long long)(k * 2 + 1) * P.B + b) * P.C + c) * plane + off]);
+__device__ __forceinline__ float direction_val(const OT* __restrict__ out_bc, long long sample_stride, int B, int k, int off,
+                                               bool fp16sem) {
+  // out_bc points at channel c of batch entry b of sample 0; sample s lives s*sample_stride further
+  const float un = ld_ro<OT>(out_bc + (long long)(k * 2 + 0) * B * sample_stride + off);
+  const float co = ld_ro<OT>(out_bc + (long long)(k * 2 + 1) * B * sample_stride + off);
   float d = __fsub_rn(co, un);                                       // ed:440
   if (fp16sem) d = __half2float(__float2half_rn(d));                 // fp16 tensor under CUDA autocast / ed:655
   return d;
 }
 
 template <typename OT>
-__device__ __forceinline__ float local_uncond_at(const ed_plan_t& P, const OT* __restrict__ out, int first_view_sample,
-                                                 int b, int c, int y, int x) {
+__device__ __noinline__ float local_uncond_walk(const ed_plan_t& P, const OT* __restrict__ out_bc, long long sample_stride,
+                                                int first_view_sample, int y, int x) {
   const int r0 = __ldg(P.vrow_first + y), rn = __ldg(P.vrow_cnt + y);
   const int c0 = __ldg(P.vcol_first + x), cn = __ldg(P.vcol_cnt + x);
-  const long long plane = (long long)P.dH * P.dW;
   float u = 0.f;
   for (int a = 0; a < rn; ++a)
     for (int e = 0; e < cn; ++e) {
       const int v = (r0 + a) * P.nvc + (c0 + e);
       const int32_t* vt = P.views + v * 8;
-      const int yy = P.v_tp + vt[6] + (y - vt[0]);
-      const int xx = P.v_lp + vt[7] + (x - vt[2]);
-      u = to_f32<OT>(out[(((long long)(first_view_sample + v * P.B + b)) * P.C + c) * plane + (long long)yy * P.dW + xx]);
+      const int yy = P.v_tp + __ldg(vt + 6) + (y - __ldg(vt + 0));
+      const int xx = P.v_lp + __ldg(vt + 7) + (x - __ldg(vt + 2));
+      u = ld_ro<OT>(out_bc + (long long)(first_view_sample + v * P.B) * sample_stride + (long long)yy * P.dW + xx);
       if (u != 0.f) return u;                                       // first writer wins where the value is non-zero (ed:859)
     }
   return u;
 }
 
-template <typename OT, int VEC>
-__global__ void __launch_bounds__(256) wave_epilogue_kernel(const EpiArgs A) {
+// grid: x over W/VEC, y over H, z over (b, channel group); thread = VEC consecutive pixels of one row, CPT channels.
+// CPT = 4 (all channels of an SD latent in one thread) is the throughput shape: the per-pixel refs are amortised over
+// the channels, the prologue loads of all channels are independent (read-only path, results kept in registers, stores
+// at the end), and the re-noise stream is fetched 4 channels x 4 steps = 16 float4 loads deep before the dependent
+// FMA chain consumes them.  CPT = 1 spreads the channels over gridDim.z (small batches: more CTAs, 8 loads deep).
+template <typename OT, int VEC, int CPT>
+__global__ void __launch_bounds__(256, ED_EPI_MINB) wave_epilogue_kernel(const EpiArgs A) {
   const ed_plan_t& P = A.P;
+  const int xv = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (xv * VEC >= P.W || y >= P.H) return;
   const ed_step_params_t& S = *A.prm;
   const OT* __restrict__ out = static_cast<const OT*>(A.unet_out);
   const int R1 = S.R1;
   const int flags = S.flags;
   const bool fp16sem = (flags & ED_FLAG_FP16_SEM) != 0;
+  const bool rrg = (flags & ED_FLAG_RRG) != 0;
   const float g = S.guidance, sb = S.sqrt_beta_t, sa = S.sqrt_alpha_t, sap = S.sqrt_alpha_prev, sd = S.sqrt_dir;
+  const float rrg_norm = S.rrg_norm, rrg_w = S.rrg_weight;
+  const int n_re = (flags & ED_FLAG_RENOISE) ? S.n_renoise : 0;
   const int first_view_sample = 2 * P.B * R1;
-  const int wv = P.W / VEC;
-  const long long total = (long long)P.B * P.C * P.H * wv;
-  const long long numel = (long long)P.B * P.C * P.H * P.W;
+  const long long hw = (long long)P.H * P.W;
+  const long long numel = (long long)P.B * P.C * hw;
   const long long plane = (long long)P.dH * P.dW;
+  const long long sample_stride = (long long)P.C * plane;
+  constexpr int KB = 16 / CPT;                                         // re-noise steps fetched per batch
 
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int xv = (int)(i % wv);
-    long long r = i / wv;
-    const int y = (int)(r % P.H);
-    r /= P.H;
-    const int c = (int)(r % P.C);
-    const int b = (int)(r / P.C);
-    const long long base = (((long long)b * P.C + c) * P.H + y) * P.W + xv * VEC;
-
-    float xin[VEC], res[VEC], x0v[VEC];
-    if constexpr (VEC == 4) {
-      const float4 t = *reinterpret_cast<const float4*>(A.latent + base);
-      xin[0] = t.x; xin[1] = t.y; xin[2] = t.z; xin[3] = t.w;
-    } else {
+  PixelRefs ref[VEC];
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) xin[e] = A.latent[base + e];
-    }
+  for (int e = 0; e < VEC; ++e) pixel_refs(P, A.idx, A.owner, R1, y * P.W + xv * VEC + e, rrg, ref[e]);
 
+  const int groups = P.C / CPT;
+  for (int z = blockIdx.z; z < P.B * groups; z += gridDim.z) {
+    const int b = z / groups, c_lo = (z - b * groups) * CPT;
+    const long long base0 = (((long long)b * P.C + c_lo) * P.H + y) * P.W + xv * VEC;   // channel c_lo; + cc*hw per channel
+    float res[CPT][VEC];
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) {
-      const int x = xv * VEC + e;
-      const float u = local_uncond_at<OT>(P, out, first_view_sample, b, c, y, x);
-      const float d = direction_at<OT>(P, out, A.idx, R1, b, c, y, x, fp16sem);
-      float gd = __fmul_rn(g, d);
-      if (fp16sem) gd = __half2float(__float2half_rn(gd));          // python float * fp16 tensor -> fp16
-      const float eps = __fadd_rn(u, gd);                            // ed:1031
-      const float x0 = __fdiv_rn(__fsub_rn(xin[e], __fmul_rn(sb, eps)), sa);   // DDIM "predicted x_0"
-      const float xp = __fadd_rn(__fmul_rn(sap, x0), __fmul_rn(sd, eps));      // x_{t-1}, eta = 0
-      x0v[e] = x0;
-      res[e] = xp;
-
-      if (flags & ED_FLAG_RRG) {
-        // reference low-res x0 of the LAST resampling iteration at the cell that nearest-upsampling reads (ed:909-922)
-        const int kl = R1 - 1;
-        const int ur = __ldg(P.up_row + y), uc = __ldg(P.up_col + x);
-        const int pick = A.idx[((long long)kl * P.lh + ur) * P.lw + uc];
-        const int sr = __ldg(P.row_src + 2 * ur + (pick >> 1)), sc = __ldg(P.col_src + 2 * uc + (pick & 1));
-        const float xl = A.latent[(((long long)b * P.C + c) * P.H + sr) * P.W + sc];
-        const float ul = to_f32<OT>(out[(((long long)(kl * 2) * P.B + b) * P.C + c) * plane +
-                                        (long long)(P.g_tp + ur) * P.dW + P.g_lp + uc]);
-        // downsampled_direction = nearest-down of the filled full-res direction (ed:688)
-        const float dl = direction_at<OT>(P, out, A.idx, R1, b, c, __ldg(P.down_row + ur), __ldg(P.down_col + uc), fp16sem);
-        float gl = __fmul_rn(g, dl);
-        float el;
-        float t1;
-        if (fp16sem) {
-          gl = __half2float(__float2half_rn(gl));
-          el = __half2float(__float2half_rn(__fadd_rn(ul, gl)));     // fp16 + fp16 (ed:918)
-          t1 = __half2float(__float2half_rn(__fmul_rn(sb, el)));     // 0-dim fp32 tensor * fp16 tensor -> fp16
-        } else {
-          el = __fadd_rn(ul, gl);
-          t1 = __fmul_rn(sb, el);
-        }
-        const float ref = __fdiv_rn(__fsub_rn(xl, t1), sa);          // ed:920-921
-        // -d/dx0 [ w * mse(ref_up, x0) ] = -( (2/N) * (x0 - ref) * w )   (mse_loss backward, ed:932-935)
-        const float grad = __fmul_rn(__fmul_rn(S.rrg_norm, __fsub_rn(x0, ref)), S.rrg_weight);
-        res[e] = __fadd_rn(xp, -grad);                               // ed:1078
+    for (int cc = 0; cc < CPT; ++cc) {
+      const long long base = base0 + cc * hw;
+      const float* lat_plane = A.latent + ((long long)b * P.C + c_lo + cc) * hw;
+      const OT* out_bc = out + ((long long)b * P.C + c_lo + cc) * plane;   // sample 0, batch entry b, channel c
+      float xin[VEC];
+      if constexpr (VEC == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(A.latent + base));
+        xin[0] = t.x; xin[1] = t.y; xin[2] = t.z; xin[3] = t.w;
+      } else {
+        xin[0] = __ldg(A.latent + base);
       }
-    }
-
-    if (flags & ED_FLAG_RENOISE) {                                   // ed:692-704, sequential like the reference
-      const int n = S.n_renoise;
-      for (int k = 0; k < n; ++k) {
-        const float a = S.renoise_a[k], bb = S.renoise_b[k];
-        float nz[VEC];
-        if constexpr (VEC == 4) {
-          const float4 t = __ldcs(reinterpret_cast<const float4*>(A.noise + (long long)k * numel + base));
-          nz[0] = t.x; nz[1] = t.y; nz[2] = t.z; nz[3] = t.w;
-        } else {
-#pragma unroll
-          for (int e = 0; e < VEC; ++e) nz[e] = A.noise[(long long)k * numel + base + e];
-        }
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) res[e] = __fadd_rn(__fmul_rn(a, res[e]), __fmul_rn(bb, nz[e]));
-      }
-    }
-
-    if constexpr (VEC == 4) {
-      *reinterpret_cast<float4*>(A.out_latent + base) = make_float4(res[0], res[1], res[2], res[3]);
-      if (A.out_x0) *reinterpret_cast<float4*>(A.out_x0 + base) = make_float4(x0v[0], x0v[1], x0v[2], x0v[3]);
-    } else {
+      float x0v[VEC];
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
-        A.out_latent[base + e] = res[e];
-        if (A.out_x0) A.out_x0[base + e] = x0v[e];
+        float u;
+        if (ref[e].view >= 0) {
+          u = ld_ro<OT>(out_bc + (long long)(first_view_sample + ref[e].view * P.B) * sample_stride + ref[e].view_off);
+        } else {
+          u = local_uncond_walk<OT>(P, out_bc, sample_stride, first_view_sample, y, xv * VEC + e);
+        }
+        const float d = direction_val<OT>(out_bc, sample_stride, P.B, ref[e].dir_k, ref[e].dir_off, fp16sem);
+        float gd = __fmul_rn(g, d);
+        if (fp16sem) gd = __half2float(__float2half_rn(gd));          // python float * fp16 tensor -> fp16
+        const float eps = __fadd_rn(u, gd);                            // ed:1031
+        const float x0 = __fdiv_rn(__fsub_rn(xin[e], __fmul_rn(sb, eps)), sa);   // DDIM "predicted x_0"
+        const float xp = __fadd_rn(__fmul_rn(sap, x0), __fmul_rn(sd, eps));      // x_{t-1}, eta = 0
+        x0v[e] = x0;
+        res[cc][e] = xp;
+        if (rrg) {
+          // reference low-res x0 of the LAST resampling iteration at the cell nearest-upsampling reads (ed:909-922)
+          const int kl = R1 - 1;
+          const float xl = __ldg(lat_plane + ref[e].lat_off);
+          const float ul = ld_ro<OT>(out_bc + (long long)(kl * 2) * P.B * sample_stride + ref[e].dir_off);
+          // downsampled_direction = nearest-down of the filled full-res direction (ed:688)
+          const float dl = direction_val<OT>(out_bc, sample_stride, P.B, ref[e].ddir_k, ref[e].ddir_off, fp16sem);
+          float gl = __fmul_rn(g, dl);
+          float el, t1;
+          if (fp16sem) {
+            gl = __half2float(__float2half_rn(gl));
+            el = __half2float(__float2half_rn(__fadd_rn(ul, gl)));     // fp16 + fp16 (ed:918)
+            t1 = __half2float(__float2half_rn(__fmul_rn(sb, el)));     // 0-dim fp32 tensor * fp16 tensor -> fp16
+          } else {
+            el = __fadd_rn(ul, gl);
+            t1 = __fmul_rn(sb, el);
+          }
+          const float rx0 = __fdiv_rn(__fsub_rn(xl, t1), sa);          // ed:920-921
+          // -d/dx0 [ w * mse(ref_up, x0) ] = -( (2/N) * (x0 - ref) * w )   (mse_loss backward, ed:932-935)
+          const float grad = __fmul_rn(__fmul_rn(rrg_norm, __fsub_rn(x0, rx0)), rrg_w);
+          res[cc][e] = __fadd_rn(xp, -grad);                           // ed:1078
+        }
       }
+      if (A.out_x0) {
+        if constexpr (VEC == 4) *reinterpret_cast<float4*>(A.out_x0 + base) = make_float4(x0v[0], x0v[1], x0v[2], x0v[3]);
+        else A.out_x0[base] = x0v[0];
+      }
+    }
+    // ed:692-704: x <- a_k x + b_k eps_k, sequential in k like the reference.  Noise is streamed once (evict-first).
+    if (n_re > 0) {
+      const float* nz = A.noise + base0;
+      int k = 0;
+      if constexpr (VEC == 4) {
+        for (; k + KB <= n_re; k += KB) {
+          float4 t[CPT][KB];
+#pragma unroll
+          for (int cc = 0; cc < CPT; ++cc)
+#pragma unroll
+            for (int j = 0; j < KB; ++j)
+              t[cc][j] = __ldcs(reinterpret_cast<const float4*>(nz + (long long)(k + j) * numel + cc * hw));
+#pragma unroll
+          for (int j = 0; j < KB; ++j) {
+            const float a = S.renoise_a[k + j], bb = S.renoise_b[k + j];
+#pragma unroll
+            for (int cc = 0; cc < CPT; ++cc) {
+              res[cc][0] = __fadd_rn(__fmul_rn(a, res[cc][0]), __fmul_rn(bb, t[cc][j].x));
+              res[cc][1] = __fadd_rn(__fmul_rn(a, res[cc][1]), __fmul_rn(bb, t[cc][j].y));
+              res[cc][2] = __fadd_rn(__fmul_rn(a, res[cc][2]), __fmul_rn(bb, t[cc][j].z));
+              res[cc][3] = __fadd_rn(__fmul_rn(a, res[cc][3]), __fmul_rn(bb, t[cc][j].w));
+            }
+          }
+        }
+      }
+      for (; k < n_re; ++k) {
+        const float a = S.renoise_a[k], bb = S.renoise_b[k];
+#pragma unroll
+        for (int cc = 0; cc < CPT; ++cc) {
+          if constexpr (VEC == 4) {
+            const float4 t = __ldcs(reinterpret_cast<const float4*>(nz + (long long)k * numel + cc * hw));
+            res[cc][0] = __fadd_rn(__fmul_rn(a, res[cc][0]), __fmul_rn(bb, t.x));
+            res[cc][1] = __fadd_rn(__fmul_rn(a, res[cc][1]), __fmul_rn(bb, t.y));
+            res[cc][2] = __fadd_rn(__fmul_rn(a, res[cc][2]), __fmul_rn(bb, t.z));
+            res[cc][3] = __fadd_rn(__fmul_rn(a, res[cc][3]), __fmul_rn(bb, t.w));
+          } else {
+            res[cc][0] = __fadd_rn(__fmul_rn(a, res[cc][0]), __fmul_rn(bb, __ldcs(nz + (long long)k * numel + cc * hw)));
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int cc = 0; cc < CPT; ++cc) {
+      if constexpr (VEC == 4)
+        *reinterpret_cast<float4*>(A.out_latent + base0 + cc * hw) = make_float4(res[cc][0], res[cc][1], res[cc][2], res[cc][3]);
+      else
+        A.out_latent[base0 + cc * hw] = res[cc][0];
     }
   }
 }
@@ -235,24 +307,44 @@ using namespace ed;
 
 extern "C" {
 
+int ed_owner_map(const ed_plan_t* plan, int R1, const uint8_t* idx, uint8_t* owner, void* stream_) {
+  if (!plan || !idx || !owner || R1 <= 0 || R1 > 255) return ED_ERR_INVALID;
+  const ed_plan_t& P = *plan;
+  if (!P.mrow_lo || !P.mrow_n || !P.mcol_lo || !P.mcol_n) return ED_ERR_INVALID;
+  const dim3 block(32, 8), grid((P.W + 31) / 32, (P.H + 7) / 8);
+  owner_map_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream_)>>>(P, R1, idx, owner);
+  ED_LAUNCH_CHECK();
+  return ED_OK;
+}
+
 int ed_wave_epilogue(const ed_plan_t* plan, const ed_step_params_t* d_params, const float* latent, const void* unet_out,
-                     int out_dtype, const uint8_t* idx, const float* noise, float* out_latent, float* out_x0,
-                     void* stream_) {
-  if (!plan || !d_params || !latent || !unet_out || !idx || !out_latent) return ED_ERR_INVALID;
+                     int out_dtype, const uint8_t* idx, const uint8_t* owner, const float* noise, float* out_latent,
+                     float* out_x0, void* stream_) {
+  if (!plan || !d_params || !latent || !unet_out || !idx || !owner || !out_latent) return ED_ERR_INVALID;
   const ed_plan_t& P = *plan;
   if (!P.mrow_lo || !P.mrow_n || !P.mcol_lo || !P.mcol_n || !P.up_row || !P.up_col || !P.down_row || !P.down_col ||
-      !P.views || !P.vrow_first || !P.vrow_cnt || !P.vcol_first || !P.vcol_cnt || !P.row_src || !P.col_src)
+      !P.views || !P.vrow_first || !P.vrow_cnt || !P.vcol_first || !P.vcol_cnt || !P.row_src || !P.col_src ||
+      !P.pix_ref || !P.cell_cand || !P.cell_down)
     return ED_ERR_INVALID;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  EpiArgs A{P, d_params, latent, unet_out, idx, noise, out_latent, out_x0};
+  // channels per thread: 4 when the batch alone fills the GPU, 1 (channels spread over gridDim.z) for small batches
+  const int cpt = (P.C % 4 == 0 && P.B >= 8) ? 4 : 1;
+  const int c_split = P.C / cpt;
+  EpiArgs A{P, d_params, latent, unet_out, idx, owner, noise, out_latent, out_x0};
   auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const bool vec = (P.W % 4 == 0) && aligned(latent) && aligned(out_latent) && (!out_x0 || aligned(out_x0)) &&
                    (!noise || aligned(noise));
-  const long long total = (long long)P.B * P.C * P.H * (vec ? P.W / 4 : P.W);
-  const int g = epi_grid(total);
-#define ED_EPI(T)                                                     \
-  if (vec) wave_epilogue_kernel<T, 4><<<g, 256, 0, stream>>>(A);       \
-  else wave_epilogue_kernel<T, 1><<<g, 256, 0, stream>>>(A);
+  const int wv = vec ? P.W / 4 : P.W;
+  int bx = 32;
+  while (bx > 1 && bx / 2 >= wv) bx /= 2;                 // narrow rows: fewer idle lanes
+  const dim3 block(bx, 256 / bx);
+  const dim3 grid((wv + block.x - 1) / block.x, (P.H + block.y - 1) / block.y,
+                  P.B * c_split > 65535 ? 65535 : P.B * c_split);
+#define ED_EPI(T)                                                                       \
+  if (vec && cpt == 4) wave_epilogue_kernel<T, 4, 4><<<grid, block, 0, stream>>>(A);     \
+  else if (vec) wave_epilogue_kernel<T, 4, 1><<<grid, block, 0, stream>>>(A);            \
+  else if (cpt == 4) wave_epilogue_kernel<T, 1, 4><<<grid, block, 0, stream>>>(A);       \
+  else wave_epilogue_kernel<T, 1, 1><<<grid, block, 0, stream>>>(A);
   switch (out_dtype) {
     case ED_F32: ED_EPI(float) break;
     case ED_F16: ED_EPI(__half) break;

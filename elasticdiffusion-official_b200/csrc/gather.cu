@@ -154,46 +154,67 @@ __device__ __forceinline__ float pad_value(const Strips& S, int c, int Y, int X,
   return S.p[1][((long long)c * ih + ly) * (dW - lp - iw) + (lx - iw)];
 }
 
+// grid: x over vector-columns of the canvas, y over canvas rows, z over (b, c) planes.  A thread owns VEC canvas
+// columns of one row of plane (b, c) for ALL R1 resampling iterations: inside the low-res box it reads the 2x2
+// candidate pixels of its VEC cells ONCE (the latent is read once per wave, not once per iteration) and emits the
+// picked value per iteration; outside it reads the background strip value once (strips are shared by every sample).
+// Either way it then issues 2*R1 vector stores (uncond + cond copies, ed:436).
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) pick_gather_kernel(const ed_plan_t P, int R1, const float* __restrict__ latent,
                                                           const uint8_t* __restrict__ idx, const Strips S,
                                                           T* __restrict__ canvas) {
-  const int wv = P.dW / VEC;
-  const long long total = (long long)R1 * P.B * P.C * P.dH * wv;
+  const int xv = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (Y >= P.dH || xv * VEC >= P.dW) return;
+  const int n_planes = P.B * P.C;
   const long long plane = (long long)P.dH * P.dW;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int xv = (int)(i % wv);
-    long long r = i / wv;
-    int Y = (int)(r % P.dH);
-    r /= P.dH;
-    int c = (int)(r % P.C);
-    r /= P.C;
-    int b = (int)(r % P.B);
-    int k = (int)(r / P.B);
-    float v[VEC];
-    const int ly = Y - P.g_tp;
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) {
-      const int X = xv * VEC + e, lx = X - P.g_lp;
-      if (ly >= 0 && ly < P.lh && lx >= 0 && lx < P.lw) {
-        const int pick = idx[((long long)k * P.lh + ly) * P.lw + lx];
-        const int sr = __ldg(P.row_src + 2 * ly + (pick >> 1));
-        const int sc = __ldg(P.col_src + 2 * lx + (pick & 1));
-        v[e] = __ldg(latent + (((long long)b * P.C + c) * P.H + sr) * P.W + sc);
-      } else {
-        v[e] = pad_value(S, c, Y, X, P.g_tp, P.g_lp, P.lh, P.lw, P.dH, P.dW);
-      }
-    }
-    T* o0 = canvas + (((long long)(k * 2 + 0) * P.B + b) * P.C + c) * plane + (long long)Y * P.dW + xv * VEC;
-    T* o1 = canvas + (((long long)(k * 2 + 1) * P.B + b) * P.C + c) * plane + (long long)Y * P.dW + xv * VEC;
-    if constexpr (VEC == 4) {
-      store4<T>(o0, v);
-      store4<T>(o1, v);
-    } else {
+  const long long kstride = (long long)n_planes * plane;               // one block of B samples
+  const int cells = P.lh * P.lw;
+  const int ly = Y - P.g_tp, lx0 = xv * VEC - P.g_lp;
+  const bool inner = ly >= 0 && ly < P.lh && lx0 >= 0 && lx0 < P.lw;     // VEC-aligned by construction
+  for (int z = blockIdx.z; z < n_planes; z += gridDim.z) {
+    T* o = canvas + (long long)z * plane + (long long)Y * P.dW + xv * VEC;   // sample (k=0, s=0, b), channel c
+    if (inner) {
+      const float* src = latent + (long long)z * P.H * P.W;
+      const int r0 = __ldg(P.row_src + 2 * ly) * P.W, r1 = __ldg(P.row_src + 2 * ly + 1) * P.W;
+      float cand[VEC][4];
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
-        o0[e] = from_f32<T>(v[e]);
-        o1[e] = from_f32<T>(v[e]);
+        const int lx = lx0 + e;
+        const int c0 = __ldg(P.col_src + 2 * lx), c1 = __ldg(P.col_src + 2 * lx + 1);
+        cand[e][0] = __ldg(src + r0 + c0);
+        cand[e][1] = __ldg(src + r0 + c1);
+        cand[e][2] = __ldg(src + r1 + c0);
+        cand[e][3] = __ldg(src + r1 + c1);
+      }
+      const int cell0 = ly * P.lw + lx0;
+#pragma unroll 2
+      for (int k = 0; k < R1; ++k) {
+        float v[VEC];
+        if constexpr (VEC == 4) {
+          const uint32_t pk = __ldg(reinterpret_cast<const uint32_t*>(idx + k * cells + cell0));
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int p = (pk >> (8 * e)) & 3;
+            v[e] = p == 0 ? cand[e][0] : p == 1 ? cand[e][1] : p == 2 ? cand[e][2] : cand[e][3];
+          }
+          store4<T>(o + (2 * k) * kstride, v);
+          store4<T>(o + (2 * k + 1) * kstride, v);
+        } else {
+          const int p = __ldg(idx + k * cells + cell0) & 3;
+          v[0] = p == 0 ? cand[0][0] : p == 1 ? cand[0][1] : p == 2 ? cand[0][2] : cand[0][3];
+          o[(2 * k) * kstride] = from_f32<T>(v[0]);
+          o[(2 * k + 1) * kstride] = from_f32<T>(v[0]);
+        }
+      }
+    } else {
+      const int c = z % P.C;
+      float v[VEC];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) v[e] = pad_value(S, c, Y, xv * VEC + e, P.g_tp, P.g_lp, P.lh, P.lw, P.dH, P.dW);
+      for (int k = 0; k < 2 * R1; ++k) {
+        if constexpr (VEC == 4) store4<T>(o + k * kstride, v);
+        else o[k * kstride] = from_f32<T>(v[0]);
       }
     }
   }
@@ -287,12 +308,17 @@ int ed_random_pick_gather(const ed_plan_t* plan, int R1, const float* latent, co
   if (!check_strips(strips, P.g_tp, P.g_lp, P.lh, P.lw, P.dH, P.dW)) return ED_ERR_INVALID;
   for (int i = 0; i < 4; ++i) S.p[i] = strips[i];
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const bool vec = (P.dW % 4 == 0) && ((reinterpret_cast<uintptr_t>(canvas) & 15) == 0);
-  const long long total = (long long)R1 * P.B * P.C * P.dH * (vec ? P.dW / 4 : P.dW);
-  const int g = grid_for(total);
-#define ED_PICK(T)                                                                           \
-  if (vec) pick_gather_kernel<T, 4><<<g, 256, 0, stream>>>(P, R1, latent, idx, S, (T*)canvas); \
-  else pick_gather_kernel<T, 1><<<g, 256, 0, stream>>>(P, R1, latent, idx, S, (T*)canvas);
+  const bool vec = (P.dW % 4 == 0) && (P.lw % 4 == 0) && (P.g_lp % 4 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(canvas) & 15) == 0) && ((reinterpret_cast<uintptr_t>(idx) & 3) == 0);
+  const int cols = P.dW / (vec ? 4 : 1), rows = P.dH;
+  int bx = 32;
+  while (bx > 1 && bx / 2 >= cols) bx /= 2;
+  const dim3 block(bx, 256 / bx);
+  const long long planes = (long long)P.B * P.C;
+  const dim3 grid((cols + block.x - 1) / block.x, (rows + block.y - 1) / block.y, planes > 65535 ? 65535 : (int)planes);
+#define ED_PICK(T)                                                                              \
+  if (vec) pick_gather_kernel<T, 4><<<grid, block, 0, stream>>>(P, R1, latent, idx, S, (T*)canvas); \
+  else pick_gather_kernel<T, 1><<<grid, block, 0, stream>>>(P, R1, latent, idx, S, (T*)canvas);
   switch (canvas_dtype) {
     case ED_F32: ED_PICK(float) break;
     case ED_F16: ED_PICK(__half) break;

@@ -6,58 +6,93 @@
 
 namespace ed {
 
-template <typename PT, int VEC>
+// One thread produces VEC consecutive pixels of ROWS consecutive image rows of one (b, ch) plane.  ROWS rows aligned to
+// ROWS lie in the same latent row when scale % ROWS == 0, so the tile-cover lookups are shared and the ROWS patch
+// loads are independent (ROWS x VEC x sizeof(PT) bytes in flight per thread).
+template <typename PT, int VEC, int ROWS>
 __global__ void __launch_bounds__(256) tile_blend_kernel(const ed_tiles_t T, const PT* __restrict__ patches,
                                                          float* __restrict__ image) {
   const int Hp = T.H * T.scale, Wp = T.W * T.scale;
   const int side = (T.core + 2 * T.pad) * T.scale;   // decoded patch side in pixels
   const int padp = T.pad * T.scale;
-  const int wv = Wp / VEC;
-  const long long total = (long long)T.B * T.CH * Hp * wv;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int xv = (int)(i % wv);
-    long long r = i / wv;
-    const int y = (int)(r % Hp);
-    r /= Hp;
-    const int ch = (int)(r % T.CH);
-    const int b = (int)(r / T.CH);
-    const int ly = y / T.scale;
-    const int lx = (xv * VEC) / T.scale;        // VEC consecutive pixels share one latent column (scale % VEC == 0)
-    const int r0 = __ldg(T.trow_first + ly), rn = __ldg(T.trow_cnt + ly);
-    const int c0 = __ldg(T.tcol_first + lx), cn = __ldg(T.tcol_cnt + lx);
-    float acc[VEC];
+  const int xv = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * ROWS;
+  if (xv * VEC >= Wp || y0 >= Hp) return;
+  const int ly = y0 / T.scale;
+  const int lx = (xv * VEC) / T.scale;          // the VEC pixels share one latent column (scale % VEC == 0)
+  const int r0 = __ldg(T.trow_first + ly), rn = __ldg(T.trow_cnt + ly);
+  const int c0 = __ldg(T.tcol_first + lx), cn = __ldg(T.tcol_cnt + lx);
+  const int icnt = rn * cn;                                          // count[...] += 1 per covering tile (ed:307)
+  const float cnt = (float)icnt;
+  // image / count: for power-of-two counts (1, 2, 4 - everything but the shifted last tiles of low_vram decoding) the
+  // IEEE quotient equals the product with the exact reciprocal; the ~30-instruction division is kept for the rest
+  const bool pow2 = (icnt & (icnt - 1)) == 0;
+  const float rcp = 1.0f / cnt;
+  for (int z = blockIdx.z; z < T.B * T.CH; z += gridDim.z) {
+    const int b = z / T.CH, ch = z - b * T.CH;
+    float acc[ROWS][VEC];
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) acc[r][e] = 0.f;
     for (int a = 0; a < rn; ++a)
-      for (int q = 0; q < cn; ++q) {
+      for (int q = 0; q < cn; ++q) {                                   // ascending tile order = the reference's += order
         const int j = (r0 + a) * T.ntc + (c0 + q);
         const int h0 = __ldg(T.tiles + j * 4 + 0), w0 = __ldg(T.tiles + j * 4 + 2);
-        const int py = padp + (y - h0 * T.scale);
+        const int py = padp + (y0 - h0 * T.scale);
         const int px = padp + (xv * VEC - w0 * T.scale);
         const PT* src = patches + ((((long long)j * T.B + b) * T.CH + ch) * side + py) * side + px;
-        float v[VEC];
-        if constexpr (VEC == 4 && sizeof(PT) == 4) {
-          const float4 t = __ldcs(reinterpret_cast<const float4*>(src));
-          v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-        } else {
+        float v[ROWS][VEC];
 #pragma unroll
-          for (int e = 0; e < VEC; ++e) v[e] = to_f32<PT>(src[e]);
+        for (int r = 0; r < ROWS; ++r) {
+          if (y0 + r >= Hp) break;
+          const PT* s = src + (long long)r * side;
+          if constexpr (sizeof(PT) == 4 && VEC % 4 == 0) {
+#pragma unroll
+            for (int e = 0; e < VEC; e += 4) {
+              const float4 t = __ldcs(reinterpret_cast<const float4*>(s + e));
+              v[r][e] = t.x; v[r][e + 1] = t.y; v[r][e + 2] = t.z; v[r][e + 3] = t.w;
+            }
+          } else if constexpr (sizeof(PT) == 2 && VEC == 8) {
+            const uint4 t = __ldcs(reinterpret_cast<const uint4*>(s));   // 8 x 16-bit
+            const PT* h = reinterpret_cast<const PT*>(&t);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[r][e] = to_f32<PT>(h[e]);
+          } else if constexpr (sizeof(PT) == 2 && VEC == 4) {
+            const uint2 t = __ldcs(reinterpret_cast<const uint2*>(s));   // 4 x 16-bit
+            const PT* h = reinterpret_cast<const PT*>(&t);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[r][e] = to_f32<PT>(h[e]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) v[r][e] = to_f32<PT>(s[e]);
+          }
         }
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-          float p = __fadd_rn(__fmul_rn(v[e], 0.5f), 0.5f);          // imgs / 2 + 0.5 (ed:271); x/2 == x*0.5 exactly
-          p = fminf(fmaxf(p, 0.f), 1.f);                             // .clamp(0, 1)
-          acc[e] = __fadd_rn(acc[e], p);                             // image[...] += patch (ed:306)
-        }
+        for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            float p = __fadd_rn(__fmul_rn(v[r][e], 0.5f), 0.5f);       // imgs / 2 + 0.5 (ed:271); x/2 == x*0.5 exactly
+            p = fminf(fmaxf(p, 0.f), 1.f);                             // .clamp(0, 1)
+            acc[r][e] = __fadd_rn(acc[r][e], p);                       // image[...] += patch (ed:306)
+          }
       }
-    const float cnt = (float)(rn * cn);                              // count[...] += 1 per covering tile (ed:307)
-    float* dst = image + (((long long)b * T.CH + ch) * Hp + y) * Wp + xv * VEC;
-    if constexpr (VEC == 4) {
-      *reinterpret_cast<float4*>(dst) = make_float4(__fdiv_rn(acc[0], cnt), __fdiv_rn(acc[1], cnt),
-                                                    __fdiv_rn(acc[2], cnt), __fdiv_rn(acc[3], cnt));
-    } else {
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) dst[e] = __fdiv_rn(acc[e], cnt);
+    for (int r = 0; r < ROWS; ++r) {
+      if (y0 + r >= Hp) break;
+      float* dst = image + (((long long)b * T.CH + ch) * Hp + y0 + r) * Wp + xv * VEC;
+      if constexpr (VEC % 4 == 0) {
+#pragma unroll
+        for (int e = 0; e < VEC; e += 4)
+          __stcs(reinterpret_cast<float4*>(dst + e),
+                 pow2 ? make_float4(__fmul_rn(acc[r][e], rcp), __fmul_rn(acc[r][e + 1], rcp), __fmul_rn(acc[r][e + 2], rcp),
+                                    __fmul_rn(acc[r][e + 3], rcp))
+                      : make_float4(__fdiv_rn(acc[r][e], cnt), __fdiv_rn(acc[r][e + 1], cnt), __fdiv_rn(acc[r][e + 2], cnt),
+                                    __fdiv_rn(acc[r][e + 3], cnt)));
+      } else {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) dst[e] = pow2 ? __fmul_rn(acc[r][e], rcp) : __fdiv_rn(acc[r][e], cnt);
+      }
     }
   }
 }
@@ -74,16 +109,19 @@ extern "C" int ed_tile_blend(const ed_tiles_t* tiles, const void* patches, int p
       T.scale <= 0 || T.B <= 0 || T.CH <= 0)
     return ED_ERR_INVALID;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const int Wp = T.W * T.scale;
-  const bool vec = (T.scale % 4 == 0) && ((reinterpret_cast<uintptr_t>(image) & 15) == 0) &&
-                   ((reinterpret_cast<uintptr_t>(patches) & 15) == 0);
-  const long long total = (long long)T.B * T.CH * T.H * T.scale * (vec ? Wp / 4 : Wp);
-  long long g = (total + 255) / 256;
-  if (g > 148 * 16) g = 148 * 16;
-  if (g < 1) g = 1;
-#define ED_BLEND(PT)                                                                            \
-  if (vec) tile_blend_kernel<PT, 4><<<(int)g, 256, 0, stream>>>(T, (const PT*)patches, image);   \
-  else tile_blend_kernel<PT, 1><<<(int)g, 256, 0, stream>>>(T, (const PT*)patches, image);
+  const int Wp = T.W * T.scale, Hp = T.H * T.scale;
+  const bool al = ((reinterpret_cast<uintptr_t>(image) & 15) == 0) && ((reinterpret_cast<uintptr_t>(patches) & 15) == 0);
+  const int vec = (al && T.scale % 8 == 0) ? 8 : (al && T.scale % 4 == 0) ? 4 : 1;
+  const int rows_per = (T.scale % 4 == 0) ? 4 : 1;
+  const int cols = Wp / vec, rows = (Hp + rows_per - 1) / rows_per;
+  const dim3 block(32, 8);
+  const int planes = T.B * T.CH;
+  const dim3 g((cols + 31) / 32, (rows + 7) / 8, planes > 65535 ? 65535 : planes);
+#define ED_BLEND(PT)                                                                                 \
+  if (vec == 8) tile_blend_kernel<PT, 8, 4><<<g, block, 0, stream>>>(T, (const PT*)patches, image);    \
+  else if (vec == 4) tile_blend_kernel<PT, 4, 4><<<g, block, 0, stream>>>(T, (const PT*)patches, image); \
+  else if (rows_per == 4) tile_blend_kernel<PT, 1, 4><<<g, block, 0, stream>>>(T, (const PT*)patches, image); \
+  else tile_blend_kernel<PT, 1, 1><<<g, block, 0, stream>>>(T, (const PT*)patches, image);
   switch (patch_dtype) {
     case ED_F32: ED_BLEND(float) break;
     case ED_F16: ED_BLEND(__half) break;

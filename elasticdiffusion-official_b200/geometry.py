@@ -195,10 +195,29 @@ def build_geometry(B, C, H, W, native, ds, window, stride, context) -> WaveGeome
     vtp, vbp = pad_split(native, vh)
     vlp, vrp = pad_split(native, vw)
     g = WaveGeometry(B, C, H, W, native, lh, lw, (lp, rp, tp, bp), wins, nvr, nvc, vh, vw, (vlp, vrp, vtp, vbp))
+    up_row, up_col = nearest_index(lh, H), nearest_index(lw, W)
+    down_row, down_col = nearest_index(H, lh), nearest_index(W, lw)
     g.tables = dict(row_src=row_src, col_src=col_src, mrow_lo=mrow_lo, mrow_n=mrow_n, mcol_lo=mcol_lo, mcol_n=mcol_n,
-                    up_row=nearest_index(lh, H), up_col=nearest_index(lw, W),
-                    down_row=nearest_index(H, lh), down_col=nearest_index(W, lw),
+                    up_row=up_row, up_col=up_col, down_row=down_row, down_col=down_col,
                     views=vt, vrow_first=vrow_first, vrow_cnt=vrow_cnt, vcol_first=vcol_first, vcol_cnt=vcol_cnt)
+    # static per-pixel / per-cell references (what the epilogue would otherwise re-derive per pixel, per channel)
+    dir_off = lambda y, x: (tp + up_row[y]) * native + lp + up_col[x]
+    pix = []
+    for y in range(H):
+        for x in range(W):
+            if vrow_cnt[y] == 1 and vcol_cnt[x] == 1:
+                v = vrow_first[y] * nvc + vcol_first[x]
+                h0, _, w0, _, _, _, n_t, n_l = vt[v * 8:v * 8 + 8]
+                voff = (vtp + n_t + (y - h0)) * native + vlp + n_l + (x - w0)
+            else:
+                v, voff = -1, 0
+            pix += [dir_off(y, x), v, voff, up_row[y] * lw + up_col[x]]
+    cand, down = [], []
+    for r in range(lh):
+        for c in range(lw):
+            cand += [row_src[2 * r + (j >> 1)] * W + col_src[2 * c + (j & 1)] for j in range(4)]
+            down += [down_row[r] * W + down_col[c], dir_off(down_row[r], down_col[c])]
+    g.tables.update(pix_ref=pix, cell_cand=cand, cell_down=down)
     return g
 
 

@@ -30,7 +30,8 @@ class Plan(C.Structure):
                  "v_tp", "v_lp", "reserved0")] + \
                [(n, C.c_void_p) for n in
                 ("row_src", "col_src", "mrow_lo", "mrow_n", "mcol_lo", "mcol_n", "up_row", "up_col", "down_row",
-                 "down_col", "views", "vrow_first", "vrow_cnt", "vcol_first", "vcol_cnt")]
+                 "down_col", "views", "vrow_first", "vrow_cnt", "vcol_first", "vcol_cnt", "pix_ref", "cell_cand",
+                 "cell_down")]
 
 
 class StepParams(C.Structure):
@@ -58,8 +59,9 @@ EXPORTS = {
     "ed_random_pick_gather": (C.c_int, [C.POINTER(Plan), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
                                         C.c_void_p, C.c_int, C.c_void_p]),
     "ed_pad_views": (C.c_int, [C.POINTER(Plan), C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "ed_owner_map": (C.c_int, [C.POINTER(Plan), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ed_wave_epilogue": (C.c_int, [C.POINTER(Plan), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
-                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ed_renoise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ed_tile_gather": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                  C.c_int, C.c_void_p, C.c_void_p]),
@@ -78,6 +80,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = os.environ.get("NVCC", "nvcc")
     cmd = [nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
            "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(_ROOT, "include"), "-o", LIB_PATH] + srcs
+    cmd[1:1] = os.environ.get("ED_NVCC_FLAGS", "").split()
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -99,7 +102,7 @@ def lib():
         for name, (res, args) in EXPORTS.items():
             fn = getattr(l, name)           # AttributeError if the ABI lost a symbol
             fn.restype, fn.argtypes = res, args
-        if l.ed_abi_version() != 1:
+        if l.ed_abi_version() != 2:
             raise NativeError("libelastic_b200 ABI version mismatch")
         _lib = l
     return _lib

@@ -127,6 +127,24 @@ class RngLedger:
         self.rng_dev = owner.rng_device if owner.rng_device is not None else owner.device
         self.strip_cache = {}
         self.n_cells = geo.lh * geo.lw
+        # device draws whose VALUES the host needs (drop masks, ed:541) run on a side stream so that reading them back
+        # never waits for the UNet work queued on the main stream (Philox offsets are assigned at call time on the
+        # host, so the stream a draw runs on does not change its values)
+        self._side = torch.cuda.Stream(device=self.dev) if self.rng_dev.type == "cuda" else None
+        self._side_ev = torch.cuda.Event() if self._side is not None else None
+        self._drop_pinned = torch.empty(self.n_cells, dtype=torch.int64).pin_memory() if self._side is not None else None
+
+    def _drop_draw(self):
+        """torch.randint(0, 101, (N,), device=...) of ed:541, returned on the host."""
+        n = self.n_cells
+        if self._side is None:
+            return torch.randint(0, 101, (n,), device=self.rng_dev).cpu()
+        with torch.cuda.stream(self._side):
+            d = torch.randint(0, 101, (n,), device=self.rng_dev)
+            self._drop_pinned.copy_(d, non_blocking=True)
+            self._side_ev.record(self._side)
+        self._side_ev.synchronize()
+        return self._drop_pinned.clone()
 
     # -- seeds (ed:165-171, 321-324) -----------------------------------------------------------------------------
     def _seed(self, seed):
@@ -223,7 +241,7 @@ class RngLedger:
         for k in range(resampling_steps + 1):
             if k > 0:
                 idx = self._draw_cells(exclude)
-                drop = torch.randint(0, 101, (n,), device=self.rng_dev).cpu()      # ed:541
+                drop = self._drop_draw()                                           # ed:541
                 drop[drop <= (100 * drop_p)] = 0
                 drop[drop >= (100 * drop_p)] = 1
                 prev = idx * drop + prev * (1 - drop)
@@ -300,6 +318,11 @@ class ElasticDiffusion(nn.Module):
         self.unet_batch_limit = None  # max samples per UNet call (None: the whole wave in one call)
         self.dist_group = None        # torch.distributed group to shard wave samples over (None: WORLD if initialised)
         self.shard_waves = True
+        self.unet_input_dtype = None  # dtype the gather kernels write the UNet batch in (None: fp32 like the reference)
+        self.use_cuda_graphs = False  # capture each wave's UNet forward in a CUDA graph (static canvas / text buffers)
+        self._graphs = {}
+        self.profile_kernels = False  # record CUDA-event pairs around every libelastic_b200 launch (bench.py)
+        self._kernel_events = {}
         self.last_run = {}            # counters of the last generate_image call (kernel launches, UNet calls ...)
         self._text_embeds_fn = None
         self._projection_dim = None
@@ -436,6 +459,14 @@ class ElasticDiffusion(nn.Module):
         return image
 
     # -- the hot path ---------------------------------------------------------------------------------------------------
+    def kernel_times_ms(self, reset=True):
+        """{kernel name: (launches, total ms)} from the CUDA events recorded while `profile_kernels` was on."""
+        torch.cuda.synchronize()
+        out = {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in self._kernel_events.items()}
+        if reset:
+            self._kernel_events = {}
+        return out
+
     def _require_cuda(self):
         if self.device.type != "cuda" or not torch.cuda.is_available():
             raise native.NativeError(
@@ -461,6 +492,24 @@ class ElasticDiffusion(nn.Module):
         ws = dist.get_world_size(grp)
         return (grp, dist.get_rank(grp), ws) if ws > 1 else (None, 0, 1)
 
+    def _graphed(self, key, call):
+        """Replay (capturing on first use) `call` as a CUDA graph; its inputs must live in static buffers."""
+        ent = self._graphs.get(key)
+        if ent is None:
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):                  # warm-up outside capture (cuDNN / cuBLAS plan selection)
+                for _ in range(2):
+                    call()
+            cur.wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = call()
+            ent = self._graphs[key] = (g, out)
+        ent[0].replay()
+        return ent[1]
+
     def _unet(self, canvas, t, text, pooled, time_ids):
         """One batched UNet evaluation of a wave (dense part, through PyTorch; ed:417-426 for the XL kwargs).
         With torch.distributed initialised the samples are sharded over ranks and all-gathered (multi-GPU)."""
@@ -473,15 +522,21 @@ class ElasticDiffusion(nn.Module):
             per, lo, hi = n, 0, n
         outs = []
         limit = self.unet_batch_limit or max(hi - lo, 1)
-        with torch.autocast("cuda", enabled=self.autocast):
-            for s in range(lo, hi, limit):
-                e = min(s + limit, hi)
-                kw = {}
-                if time_ids is not None:
-                    kw["added_cond_kwargs"] = {"text_embeds": pooled[s:e], "time_ids": time_ids[s:e]}
-                outs.append(self.unet(canvas[s:e], t, encoder_hidden_states=text[s:e], **kw)["sample"])
-                self.last_run["unet_calls"] += 1
-                self.last_run["unet_samples"] += e - s
+        for s in range(lo, hi, limit):
+            e = min(s + limit, hi)
+            kw = {}
+            if time_ids is not None:
+                kw["added_cond_kwargs"] = {"text_embeds": pooled[s:e], "time_ids": time_ids[s:e]}
+
+            def call(s=s, e=e, kw=kw):
+                with torch.autocast("cuda", enabled=self.autocast):
+                    return self.unet(canvas[s:e], t, encoder_hidden_states=text[s:e], **kw)["sample"]
+            if self.use_cuda_graphs:
+                outs.append(self._graphed(("unet", canvas.data_ptr(), text.data_ptr(), s, e), call))
+            else:
+                outs.append(call())
+            self.last_run["unet_calls"] += 1
+            self.last_run["unet_samples"] += e - s
         if ws == 1:
             out = outs[0] if len(outs) == 1 else torch.cat(outs)
             return out.contiguous()
@@ -539,7 +594,7 @@ class ElasticDiffusion(nn.Module):
     def denoise(self, prompts, negative_prompts='', height=768, width=768, num_inference_steps=50,
                 guidance_scale=10.0, resampling_steps=20, new_p=0.3, rrg_stop_t=0.2, rrg_init_weight=1000,
                 rrg_scherduler_cls=CosineScheduler, cosine_scale=3.0, repaint_sampling=True, progress=tqdm,
-                step_callback=None):
+                step_callback=None, max_steps=None):
         """The loop of ed:967-1078.  Returns (final latent (B,4,H/8,W/8) fp32 on device, image_log)."""
         self._require_cuda()
         L = native.lib()
@@ -595,7 +650,7 @@ class ElasticDiffusion(nn.Module):
             raise ValueError(f"undo_step needs {n_re} forward steps > ED_MAX_RENOISE={native.ED_MAX_RENOISE}")
         nv = geo.nv
         # static per-call buffers (addresses fixed for the whole loop)
-        in_dtype = torch.float32
+        in_dtype = self.unet_input_dtype or torch.float32
         n1, n2 = 2 * B * (R + 1) + nv * B, 2 * B + nv * B
         canvas = torch.empty(max(n1, n2), C, native_size, native_size, device=dev, dtype=in_dtype)
         x_mid, x_next = torch.empty_like(x), torch.empty_like(x)
@@ -603,7 +658,13 @@ class ElasticDiffusion(nn.Module):
         noise = torch.empty(n_re, B, C, H, W, device=dev, dtype=torch.float32)
         idx1 = torch.empty(R + 1, geo.lh * geo.lw, device=dev, dtype=torch.uint8)
         idx2 = torch.zeros(1, geo.lh * geo.lw, device=dev, dtype=torch.uint8)
+        owner1 = torch.empty(H * W, device=dev, dtype=torch.uint8)     # per-wave owner maps (ed_owner_map)
+        owner2 = torch.zeros(H * W, device=dev, dtype=torch.uint8)     # wave 2 has a single iteration: owner == 0
         d_params = torch.empty(2, ctypes.sizeof(native.StepParams), device=dev, dtype=torch.uint8)
+        t_dev = torch.zeros((), device=dev, dtype=torch.int64)     # timestep for the UNet, static address (CUDA graphs)
+        idx_pin = [torch.empty(R + 1, geo.lh * geo.lw, dtype=torch.uint8).pin_memory() for _ in range(3)]
+        idx_ev = [None, None, None]
+        self._graphs = {}
         text_pair, pool_pair = torch.cat([un_text, co_text]), torch.cat([un_pool, co_pool], dim=0)   # ed:996-997
         text1 = torch.cat([text_pair] * (R + 1) + [un_text] * nv)
         pool1 = torch.cat([pool_pair] * (R + 1) + [un_pool] * nv)
@@ -616,51 +677,86 @@ class ElasticDiffusion(nn.Module):
         rrg_norm = float(torch.tensor(2.0 / (C * H * W), dtype=torch.float64).to(torch.float32))
         image_log = {}
 
+        def launch(name, fn, *args):
+            """one libelastic_b200 kernel launch (+ optional CUDA-event bracket on the launching stream)"""
+            if self.profile_kernels:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                native.check(fn(*args), name)
+                e1.record()
+                self._kernel_events.setdefault(name, []).append((e0, e1))
+            else:
+                native.check(fn(*args), name)
+            self.last_run["kernel_launches"] += 1
+
         def run_wave(x_in, t, idx_dev, R1, strips_g, strips_v, prm, slot, noise_buf, x_out, x0_out, text, pool):
             st = native.stream_handle()
             n = 2 * B * R1 + nv * B
             cv = canvas[:n]
-            native.check(L.ed_random_pick_gather(ctypes.byref(plan), R1, native.ptr(x_in), native.ptr(idx_dev),
-                                                 native.strips_array(strips_g), native.ptr(cv),
-                                                 native.dtype_code(cv.dtype), st), "ed_random_pick_gather")
-            native.check(L.ed_gather_views(ctypes.byref(plan), native.ptr(x_in), native.ptr(cv),
-                                           native.dtype_code(cv.dtype), 2 * B * R1, st), "ed_gather_views")
-            self.last_run["kernel_launches"] += 2
+            owner = owner2
+            if R1 > 1:
+                owner = owner1
+                launch("ed_owner_map", L.ed_owner_map, ctypes.byref(plan), R1, native.ptr(idx_dev), native.ptr(owner), st)
+            launch("ed_random_pick_gather", L.ed_random_pick_gather, ctypes.byref(plan), R1, native.ptr(x_in),
+                   native.ptr(idx_dev), native.strips_array(strips_g), native.ptr(cv), native.dtype_code(cv.dtype), st)
+            launch("ed_gather_views", L.ed_gather_views, ctypes.byref(plan), native.ptr(x_in), native.ptr(cv),
+                   native.dtype_code(cv.dtype), 2 * B * R1, st)
             if any(s is not None for s in strips_v):
-                native.check(L.ed_pad_views(ctypes.byref(plan), native.strips_array(strips_v), native.ptr(cv),
-                                            native.dtype_code(cv.dtype), 2 * B * R1, st), "ed_pad_views")
-                self.last_run["kernel_launches"] += 1
-            out = self._unet(cv, t, text[:n], pool[:n], None if time_ids is None else time_ids[:n])
+                launch("ed_pad_views", L.ed_pad_views, ctypes.byref(plan), native.strips_array(strips_v), native.ptr(cv),
+                       native.dtype_code(cv.dtype), 2 * B * R1, st)
+            out = self._unet(cv, t_dev, text[:n], pool[:n], None if time_ids is None else time_ids[:n])
             if out.dtype == torch.float16:
                 prm.flags |= native.FLAG_FP16_SEM
             native.check(L.ed_upload_step_params(native.ptr(d_params[slot]), ctypes.byref(prm), st), "upload")
-            native.check(L.ed_wave_epilogue(ctypes.byref(plan), native.ptr(d_params[slot]), native.ptr(x_in),
-                                            native.ptr(out), native.dtype_code(out.dtype), native.ptr(idx_dev),
-                                            native.ptr(noise_buf), native.ptr(x_out), native.ptr(x0_out), st),
-                         "ed_wave_epilogue")
-            self.last_run["kernel_launches"] += 1
+            launch("ed_wave_epilogue" + ("+renoise" if prm.flags & 1 else "+rrg" if prm.flags & 2 else ""),
+                   L.ed_wave_epilogue, ctypes.byref(plan), native.ptr(d_params[slot]), native.ptr(x_in),
+                   native.ptr(out), native.dtype_code(out.dtype), native.ptr(idx_dev), native.ptr(owner),
+                   native.ptr(noise_buf), native.ptr(x_out), native.ptr(x0_out), st)
             return out
 
-        for i, t in enumerate(progress(ts)):
+        def plan_step(i):
+            """All RNG of step i in the reference's order; touches no UNet output, so it is
+            issued one step AHEAD and overlaps with the GPU work of step i-1."""
+            t = ts[i]
             last = i == len(ts) - 1
             repaint = bool(repaint_sampling and R > 0 and not last)                            # ed:1038
-            w = rrg_w(i)
-            rrg_on = w > 10                                                                    # ed:1062
-            sc = step_scalars(self.scheduler, t)
-
-            # ---- RNG ledger of the step, in the reference's order (Appendix B of SURVEY.md) -----------------------------
-            idx_host, strips_g = ledger.global_pass(t, R, 1 - new_p)                            # ed:1016
-            strips_v = ledger.local_pass(t, self.view_batch_size)                               # ed:1027
-            idx1.copy_(idx_host)
+            p = dict(t=t, repaint=repaint, w=rrg_w(i), sc=step_scalars(self.scheduler, t))
+            idx_host, p["strips_g"] = ledger.global_pass(t, R, 1 - new_p)                       # ed:1016
+            p["strips_v"] = ledger.local_pass(t, self.view_batch_size)                          # ed:1027
+            slot = i % 3
+            if idx_ev[slot] is not None:
+                idx_ev[slot].synchronize()             # the H2D copy that last used this pinned buffer has run
+            idx_pin[slot].copy_(idx_host)
+            p["slot"] = slot
             if repaint:
                 ledger.undo_noise(n_re, (B, C, H, W), noise)                                   # ed:1040
-                _, strips_g2 = ledger.global_pass(t, 0, 1 - new_p)                              # ed:1043
-                strips_v2 = ledger.local_pass(t, self.view_batch_size)                          # ed:1049
+                _, p["strips_g2"] = ledger.global_pass(t, 0, 1 - new_p)                         # ed:1043
+                p["strips_v2"] = ledger.local_pass(t, self.view_batch_size)                     # ed:1049
+                p["renoise"] = renoise_scalars(self.scheduler, ts[i + 1])
+            return p
+
+        steps = list(enumerate(progress(ts)))
+        if max_steps is not None:
+            steps = steps[:max_steps]
+        # NOTE on buffer reuse: `noise` and `idx1` are single device buffers; the draws / copies of step i+1 are
+        # enqueued on the main stream AFTER the kernels of step i, so stream order protects them.
+        nxt = None
+        for i, t in steps:
+            p = nxt if nxt is not None else plan_step(i)
+            nxt = None
+            repaint, w, sc = p["repaint"], p["w"], p["sc"]
+            rrg_on = w > 10                                                                    # ed:1062
+            strips_g, strips_v = p["strips_g"], p["strips_v"]
+            idx1.copy_(idx_pin[p["slot"]], non_blocking=True)
+            idx_ev[p["slot"]] = torch.cuda.Event()
+            idx_ev[p["slot"]].record()
+            t_dev.fill_(int(t))
 
             # ---- wave 1 ----------------------------------------------------------------------------------------------------
             prm = native.StepParams(guidance=guidance_scale, rrg_weight=float(w), rrg_norm=rrg_norm, R1=R + 1, **sc)
             if repaint:
-                a, b = renoise_scalars(self.scheduler, ts[i + 1])
+                strips_g2, strips_v2 = p["strips_g2"], p["strips_v2"]
+                a, b = p["renoise"]
                 prm.flags = native.FLAG_RENOISE
                 prm.n_renoise = n_re
                 for k in range(n_re):
@@ -673,6 +769,8 @@ class ElasticDiffusion(nn.Module):
             else:
                 prm.flags = native.FLAG_RRG if rrg_on else 0
                 run_wave(x, t, idx1, R + 1, strips_g, strips_v, prm, 0, None, x_next, x0_buf, text1, pool1)
+            if i + 1 < len(ts) and (max_steps is None or i + 1 < max_steps):
+                nxt = plan_step(i + 1)          # look-ahead: host RNG chain of the next step runs under this step's GPU work
             x, x_next = x_next, x                                                              # ed:1078
             self.last_run["steps"] += 1
             if self.verbose and i % self.log_freq == 0:

@@ -38,11 +38,17 @@ class _Config(dict):
 
 
 def _seeded_(module: nn.Module, seed: int, scale: float = 1.0) -> None:
-    g = torch.Generator(device="cpu").manual_seed(seed)
+    """fan-in scaled normal init from an explicit generator (CPU generator for CPU modules: reproducible across
+    machines; device generator for modules built directly on a GPU: fast, used by the throughput stand-in only)."""
+    gens = {}
     with torch.no_grad():
         for p in module.parameters():
+            g = gens.get(p.device)
+            if g is None:
+                g = gens[p.device] = torch.Generator(device=p.device).manual_seed(seed)
             fan_in = p[0].numel() if p.dim() > 1 else p.numel()
-            p.copy_(torch.randn(p.shape, generator=g) * (scale / math.sqrt(max(fan_in, 1))))
+            p.copy_(torch.randn(p.shape, generator=g, device=p.device, dtype=torch.float32)
+                    * (scale / math.sqrt(max(fan_in, 1))))
 
 
 def timestep_embedding(t: torch.Tensor, dim: int) -> torch.Tensor:
@@ -262,8 +268,20 @@ class StandInUNet(nn.Module):
                         add_in=6 * 8 + 32, add_time_dim=8),
     }
 
-    def __init__(self, preset="XL1.0", layers_per_block=2, head_dim=64, seed=7):
+    def __init__(self, preset="XL1.0", layers_per_block=2, head_dim=64, seed=7, device=None, dtype=None):
         super().__init__()
+        if device is not None or dtype is not None:   # build + initialise directly on the target device / dtype
+            old = torch.get_default_dtype()
+            try:
+                torch.set_default_dtype(dtype or old)
+                with torch.device(device or "cpu"):
+                    self._build(preset, layers_per_block, head_dim, seed)
+            finally:
+                torch.set_default_dtype(old)
+        else:
+            self._build(preset, layers_per_block, head_dim, seed)
+
+    def _build(self, preset, layers_per_block, head_dim, seed):
         p = self.PRESETS[preset]
         widths, depths, ctx = p["widths"], p["depths"], p["ctx"]
         self.config = _Config(sample_size=p["sample_size"], in_channels=4, cross_attention_dim=ctx)

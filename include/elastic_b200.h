@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ED_ABI_VERSION 1
+#define ED_ABI_VERSION 2
 #define ED_MAX_RENOISE 1000
 
 typedef enum {
@@ -68,6 +68,14 @@ typedef struct {
   const int32_t* vrow_cnt;  /* [H] number of consecutive covering view-grid rows */
   const int32_t* vcol_first;/* [W] */
   const int32_t* vcol_cnt;  /* [W] */
+  /* static per-pixel / per-cell references derived from the tables above (host-built once per call) so that the
+   * epilogue's per-pixel prologue is three loads instead of ~40 dependent table walks: */
+  const int32_t* pix_ref;   /* [H*W*4] dir_off (offset of the low-res cell nearest-up reads, inside a canvas plane),
+                               view (single covering view or -1), view_off (offset of the pixel in that view's canvas
+                               plane), cell (low-res cell index ur*lw+uc) */
+  const int32_t* cell_cand; /* [lh*lw*4] latent-plane offsets of the 4 candidate pixels of each 2x2 cell (ed:612-613) */
+  const int32_t* cell_down; /* [lh*lw*2] pixel index Y*W+X that nearest-DOWNsampling reads for the cell (ed:688), and
+                               the dir_off of that pixel */
 } ed_plan_t;
 
 /* Per-wave scalars, read by the epilogue kernel from DEVICE memory so that a captured CUDA graph can be replayed
@@ -123,6 +131,12 @@ int ed_random_pick_gather(const ed_plan_t* plan, int R1, const float* latent, co
 int ed_pad_views(const ed_plan_t* plan, const float* const strips[4], void* canvas, int canvas_dtype,
                  int first_sample, void* stream);
 
+/* ---- owner map: which resampling iteration's masked fill is the last to touch each full-res pixel -------------
+ * Replaces the sequence of `torch.where(mask_k, up_k, target)` over k = 0..R and the NaN back-fill (ed:637, 643-644)
+ * plus the mask restoration of restore_mask_shape (ed:446-465, 622-628): owner[y*W+x] = max{k : mask_k(y,x)} or R if no
+ * iteration sampled the pixel.  owner: (H*W) uint8, recomputed per wave from idx (R1 <= 255). */
+int ed_owner_map(const ed_plan_t* plan, int R1, const uint8_t* idx, uint8_t* owner, void* stream);
+
 /* ---- K2+K5+K6(+K7)(+K8): fused wave epilogue ---------------------------------------------------------------
  * One pass over the full-resolution latent that replaces
  *   - first-writer-wins view scatter                        compute_local_uncond_signal ed:852-861
@@ -132,11 +146,12 @@ int ed_pad_views(const ed_plan_t* plan, const float* const strips[4], void* canv
  *   - flags & ED_FLAG_RENOISE: undo_step                    ed:692-704 (noise = n_renoise torch-drawn tensors)
  *   - flags & ED_FLAG_RRG: reduced-resolution guidance      ed:886-940 and global_latent = nxt + cascade ed:1078
  * unet_out  (n_samples, C, dH, dW) of dtype out_dtype in the wave sample layout
+ * owner     (H*W) uint8 from ed_owner_map for the same idx
  * noise     [n_renoise][B*C*H*W] fp32 or NULL
  * out_latent / out_x0 fp32 (B,C,H,W); out_x0 may be NULL. */
 int ed_wave_epilogue(const ed_plan_t* plan, const ed_step_params_t* d_params, const float* latent,
-                     const void* unet_out, int out_dtype, const uint8_t* idx, const float* noise,
-                     float* out_latent, float* out_x0, void* stream);
+                     const void* unet_out, int out_dtype, const uint8_t* idx, const uint8_t* owner,
+                     const float* noise, float* out_latent, float* out_x0, void* stream);
 
 /* ---- K7 alone: x <- a_k*x + b_k*eps_k, k = 0..n-1 in sequence (ed:692-704) ---------------------------------- */
 int ed_renoise(const ed_step_params_t* d_params, const float* x, const float* noise, float* out,

@@ -25,13 +25,13 @@ def test_library_loads_and_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/elastic_b200.h but not exported"
     assert declared == set(native.EXPORTS), "ctypes binding and header disagree"
     L = native.lib()
-    assert L.ed_abi_version() == 1
+    assert L.ed_abi_version() == 2
     assert L.ed_strerror(-2).decode().startswith("unsupported")
 
 
 def test_struct_layouts_match_header_sizes():
-    # ed_plan_t: 18 int32 + 15 pointers ; ed_step_params_t: 7 float + 5 int32 + 2*ED_MAX_RENOISE float ; ed_tiles_t: 10 int32 + 5 ptr
-    assert ctypes.sizeof(native.Plan) == 18 * 4 + 15 * 8
+    # ed_plan_t: 18 int32 + 18 pointers ; ed_step_params_t: 7 float + 5 int32 + 2*ED_MAX_RENOISE float ; ed_tiles_t: 10 int32 + 5 ptr
+    assert ctypes.sizeof(native.Plan) == 18 * 4 + 18 * 8
     assert ctypes.sizeof(native.StepParams) == (7 + 5 + 2000) * 4
     assert ctypes.sizeof(native.Tiles) == 10 * 4 + 5 * 8
 
