@@ -102,19 +102,24 @@ __device__ __forceinline__ float direction_val(const OT* __restrict__ out_bc, lo
   return d;
 }
 
+struct ViewWalk {   // by-value subset of the plan for the rare multi-cover path (keeps the kernel parameter out of local memory)
+  const int32_t *views, *vrow_first, *vrow_cnt, *vcol_first, *vcol_cnt;
+  int nvc, v_tp, v_lp, dW, B;
+};
+
 template <typename OT>
-__device__ __noinline__ float local_uncond_walk(const ed_plan_t& P, const OT* __restrict__ out_bc, long long sample_stride,
+__device__ __forceinline__ float local_uncond_walk(const ViewWalk V, const OT* __restrict__ out_bc, long long sample_stride,
                                                 int first_view_sample, int y, int x) {
-  const int r0 = __ldg(P.vrow_first + y), rn = __ldg(P.vrow_cnt + y);
-  const int c0 = __ldg(P.vcol_first + x), cn = __ldg(P.vcol_cnt + x);
+  const int r0 = __ldg(V.vrow_first + y), rn = __ldg(V.vrow_cnt + y);
+  const int c0 = __ldg(V.vcol_first + x), cn = __ldg(V.vcol_cnt + x);
   float u = 0.f;
   for (int a = 0; a < rn; ++a)
     for (int e = 0; e < cn; ++e) {
-      const int v = (r0 + a) * P.nvc + (c0 + e);
-      const int32_t* vt = P.views + v * 8;
-      const int yy = P.v_tp + __ldg(vt + 6) + (y - __ldg(vt + 0));
-      const int xx = P.v_lp + __ldg(vt + 7) + (x - __ldg(vt + 2));
-      u = ld_ro<OT>(out_bc + (long long)(first_view_sample + v * P.B) * sample_stride + (long long)yy * P.dW + xx);
+      const int v = (r0 + a) * V.nvc + (c0 + e);
+      const int32_t* vt = V.views + v * 8;
+      const int yy = V.v_tp + __ldg(vt + 6) + (y - __ldg(vt + 0));
+      const int xx = V.v_lp + __ldg(vt + 7) + (x - __ldg(vt + 2));
+      u = ld_ro<OT>(out_bc + (long long)(first_view_sample + v * V.B) * sample_stride + (long long)yy * V.dW + xx);
       if (u != 0.f) return u;                                       // first writer wins where the value is non-zero (ed:859)
     }
   return u;
@@ -156,62 +161,101 @@ __global__ void __launch_bounds__(256, ED_EPI_MINB) wave_epilogue_kernel(const E
     const int b = z / groups, c_lo = (z - b * groups) * CPT;
     const long long base0 = (((long long)b * P.C + c_lo) * P.H + y) * P.W + xv * VEC;   // channel c_lo; + cc*hw per channel
     float res[CPT][VEC];
+    // ---- phase A: issue every load of the prologue (read-only path, all independent) before any arithmetic ------------
+    float xin[CPT][VEC], uu[CPT][VEC], dco[CPT][VEC], dun[CPT][VEC];
 #pragma unroll
     for (int cc = 0; cc < CPT; ++cc) {
-      const long long base = base0 + cc * hw;
-      const float* lat_plane = A.latent + ((long long)b * P.C + c_lo + cc) * hw;
       const OT* out_bc = out + ((long long)b * P.C + c_lo + cc) * plane;   // sample 0, batch entry b, channel c
-      float xin[VEC];
       if constexpr (VEC == 4) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(A.latent + base));
-        xin[0] = t.x; xin[1] = t.y; xin[2] = t.z; xin[3] = t.w;
+        const float4 t = __ldg(reinterpret_cast<const float4*>(A.latent + base0 + cc * hw));
+        xin[cc][0] = t.x; xin[cc][1] = t.y; xin[cc][2] = t.z; xin[cc][3] = t.w;
       } else {
-        xin[0] = __ldg(A.latent + base);
+        xin[cc][0] = __ldg(A.latent + base0 + cc * hw);
       }
-      float x0v[VEC];
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
-        float u;
-        if (ref[e].view >= 0) {
-          u = ld_ro<OT>(out_bc + (long long)(first_view_sample + ref[e].view * P.B) * sample_stride + ref[e].view_off);
-        } else {
-          u = local_uncond_walk<OT>(P, out_bc, sample_stride, first_view_sample, y, xv * VEC + e);
-        }
-        const float d = direction_val<OT>(out_bc, sample_stride, P.B, ref[e].dir_k, ref[e].dir_off, fp16sem);
+        // pixels covered by several windows (view < 0, overlapping last row / column) are patched after the load phase
+        const int v_ = ref[e].view >= 0 ? ref[e].view : 0;
+        uu[cc][e] = ld_ro<OT>(out_bc + (long long)(first_view_sample + v_ * P.B) * sample_stride + ref[e].view_off);
+        dun[cc][e] = ld_ro<OT>(out_bc + (long long)(ref[e].dir_k * 2 + 0) * P.B * sample_stride + ref[e].dir_off);
+        dco[cc][e] = ld_ro<OT>(out_bc + (long long)(ref[e].dir_k * 2 + 1) * P.B * sample_stride + ref[e].dir_off);
+      }
+    }
+    bool multi = false;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) multi |= ref[e].view < 0;
+    if (multi) {   // rare: first-writer-wins walk over the covering windows (ed:852-861)
+      const ViewWalk V{P.views, P.vrow_first, P.vrow_cnt, P.vcol_first, P.vcol_cnt, P.nvc, P.v_tp, P.v_lp, P.dW, P.B};
+#pragma unroll
+      for (int cc = 0; cc < CPT; ++cc)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e)
+          if (ref[e].view < 0)
+            uu[cc][e] = local_uncond_walk<OT>(V, out + ((long long)b * P.C + c_lo + cc) * plane, sample_stride,
+                                              first_view_sample, y, xv * VEC + e);
+    }
+    // ---- phase B: CFG + DDIM (ed:1031-1035) ------------------------------------------------------------------------------
+    float x0v[CPT][VEC];
+#pragma unroll
+    for (int cc = 0; cc < CPT; ++cc)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        float d = __fsub_rn(dco[cc][e], dun[cc][e]);                   // ed:440
+        if (fp16sem) d = __half2float(__float2half_rn(d));             // fp16 tensor under CUDA autocast / ed:655
         float gd = __fmul_rn(g, d);
-        if (fp16sem) gd = __half2float(__float2half_rn(gd));          // python float * fp16 tensor -> fp16
-        const float eps = __fadd_rn(u, gd);                            // ed:1031
-        const float x0 = __fdiv_rn(__fsub_rn(xin[e], __fmul_rn(sb, eps)), sa);   // DDIM "predicted x_0"
-        const float xp = __fadd_rn(__fmul_rn(sap, x0), __fmul_rn(sd, eps));      // x_{t-1}, eta = 0
-        x0v[e] = x0;
-        res[cc][e] = xp;
-        if (rrg) {
-          // reference low-res x0 of the LAST resampling iteration at the cell nearest-upsampling reads (ed:909-922)
-          const int kl = R1 - 1;
-          const float xl = __ldg(lat_plane + ref[e].lat_off);
-          const float ul = ld_ro<OT>(out_bc + (long long)(kl * 2) * P.B * sample_stride + ref[e].dir_off);
+        if (fp16sem) gd = __half2float(__float2half_rn(gd));           // python float * fp16 tensor -> fp16
+        const float eps = __fadd_rn(uu[cc][e], gd);                    // ed:1031
+        const float x0 = __fdiv_rn(__fsub_rn(xin[cc][e], __fmul_rn(sb, eps)), sa);   // DDIM "predicted x_0"
+        x0v[cc][e] = x0;
+        res[cc][e] = __fadd_rn(__fmul_rn(sap, x0), __fmul_rn(sd, eps));              // x_{t-1}, eta = 0
+      }
+    if (A.out_x0) {
+#pragma unroll
+      for (int cc = 0; cc < CPT; ++cc) {
+        if constexpr (VEC == 4)
+          *reinterpret_cast<float4*>(A.out_x0 + base0 + cc * hw) = make_float4(x0v[cc][0], x0v[cc][1], x0v[cc][2], x0v[cc][3]);
+        else
+          A.out_x0[base0 + cc * hw] = x0v[cc][0];
+      }
+    }
+    // ---- RRG (ed:886-940, 1078): second load phase (low-res reference of the last iteration), then the gradient -------
+    if (rrg) {
+      const int kl = R1 - 1;
+      float xl[CPT][VEC], ul[CPT][VEC], lco[CPT][VEC], lun[CPT][VEC];
+#pragma unroll
+      for (int cc = 0; cc < CPT; ++cc) {
+        const float* lat_plane = A.latent + ((long long)b * P.C + c_lo + cc) * hw;
+        const OT* out_bc = out + ((long long)b * P.C + c_lo + cc) * plane;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          xl[cc][e] = __ldg(lat_plane + ref[e].lat_off);               // low-res latent of the last iteration (ed:910)
+          ul[cc][e] = ld_ro<OT>(out_bc + (long long)(kl * 2) * P.B * sample_stride + ref[e].dir_off);   // its uncond score
           // downsampled_direction = nearest-down of the filled full-res direction (ed:688)
-          const float dl = direction_val<OT>(out_bc, sample_stride, P.B, ref[e].ddir_k, ref[e].ddir_off, fp16sem);
+          lun[cc][e] = ld_ro<OT>(out_bc + (long long)(ref[e].ddir_k * 2 + 0) * P.B * sample_stride + ref[e].ddir_off);
+          lco[cc][e] = ld_ro<OT>(out_bc + (long long)(ref[e].ddir_k * 2 + 1) * P.B * sample_stride + ref[e].ddir_off);
+        }
+      }
+#pragma unroll
+      for (int cc = 0; cc < CPT; ++cc)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          float dl = __fsub_rn(lco[cc][e], lun[cc][e]);
+          if (fp16sem) dl = __half2float(__float2half_rn(dl));
           float gl = __fmul_rn(g, dl);
           float el, t1;
           if (fp16sem) {
             gl = __half2float(__float2half_rn(gl));
-            el = __half2float(__float2half_rn(__fadd_rn(ul, gl)));     // fp16 + fp16 (ed:918)
-            t1 = __half2float(__float2half_rn(__fmul_rn(sb, el)));     // 0-dim fp32 tensor * fp16 tensor -> fp16
+            el = __half2float(__float2half_rn(__fadd_rn(ul[cc][e], gl)));   // fp16 + fp16 (ed:918)
+            t1 = __half2float(__float2half_rn(__fmul_rn(sb, el)));          // 0-dim fp32 tensor * fp16 tensor -> fp16
           } else {
-            el = __fadd_rn(ul, gl);
+            el = __fadd_rn(ul[cc][e], gl);
             t1 = __fmul_rn(sb, el);
           }
-          const float rx0 = __fdiv_rn(__fsub_rn(xl, t1), sa);          // ed:920-921
+          const float rx0 = __fdiv_rn(__fsub_rn(xl[cc][e], t1), sa);        // ed:920-921
           // -d/dx0 [ w * mse(ref_up, x0) ] = -( (2/N) * (x0 - ref) * w )   (mse_loss backward, ed:932-935)
-          const float grad = __fmul_rn(__fmul_rn(rrg_norm, __fsub_rn(x0, rx0)), rrg_w);
-          res[cc][e] = __fadd_rn(xp, -grad);                           // ed:1078
+          const float grad = __fmul_rn(__fmul_rn(rrg_norm, __fsub_rn(x0v[cc][e], rx0)), rrg_w);
+          res[cc][e] = __fadd_rn(res[cc][e], -grad);                        // ed:1078
         }
-      }
-      if (A.out_x0) {
-        if constexpr (VEC == 4) *reinterpret_cast<float4*>(A.out_x0 + base) = make_float4(x0v[0], x0v[1], x0v[2], x0v[3]);
-        else A.out_x0[base] = x0v[0];
-      }
     }
     // ed:692-704: x <- a_k x + b_k eps_k, sequential in k like the reference.  Noise is streamed once (evict-first).
     if (n_re > 0) {
