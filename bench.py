@@ -267,6 +267,45 @@ def cpu_reference_sample(workload, threads=None):
                       f"({step_s:.2f} s)", "t_unet_b2_s": t_b2, "glue_s": glue}
 
 
+def reference_gpu_eager(workload, device, steps=2, warm=1):
+    """Informational: the reference's OWN eager PyTorch path on this GPU (oracle port = restated reference, identical op
+    sequence: per-pass UNet calls of batch 2 / nv, fp32 weights under torch.autocast fp16 like ed:1012, VAE encode per
+    padded pass, host syncs of the rejection loop) with the same stand-in UNet topology.  This is the "reference
+    single-GPU PyTorch path" BASELINE.json's 10x target refers to; the unmodified reference file cannot travel to the
+    GPU box, so its restatement is timed."""
+    from oracle import reference_port as rp
+    from oracle.ddim_restated import DDIMRestated
+    sd, preset, H, W, vb, T, R, cross, pooled = WORKLOADS[workload]
+    syn = pkg().synthetic
+    with torch.no_grad():
+        unet = syn.StandInUNet(preset, device=device, dtype=torch.float32).eval()
+        m = rp.Models(unet, syn.StubVAE().to(device), DDIMRestated(), syn.StubTextEncoder(cross, pooled, device=device), sd,
+                      device, vb, projection_dim=pooled)
+        rp.seed_all(0, device)
+        ev = []
+
+        class Stop(Exception):
+            pass
+
+        def cb(i, x, x0):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            ev.append(e)
+            if len(ev) == warm + steps:
+                raise Stop
+        try:
+            rp.denoise(m, step_callback=cb, **dict(GEN, height=H, width=W, num_inference_steps=T, resampling_steps=R))
+        except Stop:
+            pass
+        torch.cuda.synchronize()
+        sec = ev[warm - 1].elapsed_time(ev[-1]) / 1e3
+    del unet, m
+    torch.cuda.empty_cache()
+    return {"value": steps / sec, "unit": "denoise-steps/s", "ms_per_step": 1e3 * sec / steps, "steps": steps,
+            "note": "oracle port (restated reference) eager on cuda: fp32 weights + autocast fp16, 9 batch-2 + 2 batch-4 "
+                    "UNet calls and 18 VAE-stub encodes per step"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -407,6 +446,15 @@ def main():
                                          "L2-resident and latency-bound, see kernels_in_step"}
             line["roofline_all"] = roof
         if rank == 0 and world == 1:
+            del unet
+            ed.unet = None
+            ed._graphs = {}
+            torch.cuda.empty_cache()
+            try:
+                line["reference_gpu_eager"] = reference_gpu_eager(args.workload, device)
+                line["speedup_vs_reference_gpu_eager"] = value / line["reference_gpu_eager"]["value"]
+            except Exception as e:  # informational leg only
+                line["reference_gpu_eager"] = {"error": repr(e)[:200]}
             line["cpu_baseline"] = cpu_reference_sample(args.workload)
     if rank == 0:
         print(json.dumps(line))

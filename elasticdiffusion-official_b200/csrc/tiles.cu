@@ -28,70 +28,84 @@ __global__ void __launch_bounds__(256) tile_blend_kernel(const ed_tiles_t T, con
   // IEEE quotient equals the product with the exact reciprocal; the ~30-instruction division is kept for the rest
   const bool pow2 = (icnt & (icnt - 1)) == 0;
   const float rcp = 1.0f / cnt;
+  auto load_row = [&](const PT* sp, float (&v)[VEC]) {
+    if constexpr (sizeof(PT) == 4 && VEC % 4 == 0) {
+#pragma unroll
+      for (int e = 0; e < VEC; e += 4) {
+        const float4 t = __ldcs(reinterpret_cast<const float4*>(sp + e));
+        v[e] = t.x; v[e + 1] = t.y; v[e + 2] = t.z; v[e + 3] = t.w;
+      }
+    } else if constexpr (sizeof(PT) == 2 && VEC == 8) {
+      const uint4 t = __ldcs(reinterpret_cast<const uint4*>(sp));   // 8 x 16-bit
+      const PT* h = reinterpret_cast<const PT*>(&t);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = to_f32<PT>(h[e]);
+    } else if constexpr (sizeof(PT) == 2 && VEC == 4) {
+      const uint2 t = __ldcs(reinterpret_cast<const uint2*>(sp));   // 4 x 16-bit
+      const PT* h = reinterpret_cast<const PT*>(&t);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = to_f32<PT>(h[e]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) v[e] = to_f32<PT>(sp[e]);
+    }
+  };
+  auto store_row = [&](float* dst, const float (&o)[VEC]) {
+    if constexpr (VEC % 4 == 0) {
+#pragma unroll
+      for (int e = 0; e < VEC; e += 4) __stcs(reinterpret_cast<float4*>(dst + e), make_float4(o[e], o[e + 1], o[e + 2], o[e + 3]));
+    } else {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) dst[e] = o[e];
+    }
+  };
+  const int rows_here = (Hp - y0) < ROWS ? (Hp - y0) : ROWS;
   for (int z = blockIdx.z; z < T.B * T.CH; z += gridDim.z) {
     const int b = z / T.CH, ch = z - b * T.CH;
-    float acc[ROWS][VEC];
+    float* dst0 = image + (((long long)b * T.CH + ch) * Hp + y0) * Wp + xv * VEC;
+    if (icnt == 1 && rows_here == ROWS) {
+      // ---- fast path (one covering tile, the normal case): all ROWS row loads in flight, then clamp + store -------------
+      const int j = r0 * T.ntc + c0;
+      const int h0 = __ldg(T.tiles + j * 4 + 0), w0 = __ldg(T.tiles + j * 4 + 2);
+      const PT* src = patches + ((((long long)j * T.B + b) * T.CH + ch) * side + padp + (y0 - h0 * T.scale)) * side + padp +
+                      (xv * VEC - w0 * T.scale);
+      float v[ROWS][VEC];
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r)
+      for (int r = 0; r < ROWS; ++r) load_row(src + (long long)r * side, v[r]);
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) acc[r][e] = 0.f;
-    for (int a = 0; a < rn; ++a)
-      for (int q = 0; q < cn; ++q) {                                   // ascending tile order = the reference's += order
-        const int j = (r0 + a) * T.ntc + (c0 + q);
-        const int h0 = __ldg(T.tiles + j * 4 + 0), w0 = __ldg(T.tiles + j * 4 + 2);
-        const int py = padp + (y0 - h0 * T.scale);
-        const int px = padp + (xv * VEC - w0 * T.scale);
-        const PT* src = patches + ((((long long)j * T.B + b) * T.CH + ch) * side + py) * side + px;
-        float v[ROWS][VEC];
+      for (int r = 0; r < ROWS; ++r) {
 #pragma unroll
-        for (int r = 0; r < ROWS; ++r) {
-          if (y0 + r >= Hp) break;
-          const PT* s = src + (long long)r * side;
-          if constexpr (sizeof(PT) == 4 && VEC % 4 == 0) {
-#pragma unroll
-            for (int e = 0; e < VEC; e += 4) {
-              const float4 t = __ldcs(reinterpret_cast<const float4*>(s + e));
-              v[r][e] = t.x; v[r][e + 1] = t.y; v[r][e + 2] = t.z; v[r][e + 3] = t.w;
-            }
-          } else if constexpr (sizeof(PT) == 2 && VEC == 8) {
-            const uint4 t = __ldcs(reinterpret_cast<const uint4*>(s));   // 8 x 16-bit
-            const PT* h = reinterpret_cast<const PT*>(&t);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[r][e] = to_f32<PT>(h[e]);
-          } else if constexpr (sizeof(PT) == 2 && VEC == 4) {
-            const uint2 t = __ldcs(reinterpret_cast<const uint2*>(s));   // 4 x 16-bit
-            const PT* h = reinterpret_cast<const PT*>(&t);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) v[r][e] = to_f32<PT>(h[e]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) v[r][e] = to_f32<PT>(s[e]);
-          }
+        for (int e = 0; e < VEC; ++e) {
+          float p = __fadd_rn(__fmul_rn(v[r][e], 0.5f), 0.5f);         // imgs / 2 + 0.5 (ed:271); x/2 == x*0.5 exactly
+          v[r][e] = fminf(fmaxf(p, 0.f), 1.f);                         // .clamp(0, 1);  0 + p and p / 1 are exact
         }
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r)
-#pragma unroll
-          for (int e = 0; e < VEC; ++e) {
-            float p = __fadd_rn(__fmul_rn(v[r][e], 0.5f), 0.5f);       // imgs / 2 + 0.5 (ed:271); x/2 == x*0.5 exactly
-            p = fminf(fmaxf(p, 0.f), 1.f);                             // .clamp(0, 1)
-            acc[r][e] = __fadd_rn(acc[r][e], p);                       // image[...] += patch (ed:306)
-          }
+        store_row(dst0 + (long long)r * Wp, v[r]);
       }
+    } else {
+      // ---- general path (overlapping tiles / ragged bottom): one row at a time, tiles in ascending order ---------------
+#pragma unroll 1
+      for (int r = 0; r < rows_here; ++r) {
+        float acc[VEC];
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-      if (y0 + r >= Hp) break;
-      float* dst = image + (((long long)b * T.CH + ch) * Hp + y0 + r) * Wp + xv * VEC;
-      if constexpr (VEC % 4 == 0) {
+        for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
+        for (int a = 0; a < rn; ++a)
+          for (int q = 0; q < cn; ++q) {                                 // ascending tile order = the reference's += order
+            const int j = (r0 + a) * T.ntc + (c0 + q);
+            const int h0 = __ldg(T.tiles + j * 4 + 0), w0 = __ldg(T.tiles + j * 4 + 2);
+            const int py = padp + (y0 + r - h0 * T.scale);
+            const int px = padp + (xv * VEC - w0 * T.scale);
+            float v[VEC];
+            load_row(patches + ((((long long)j * T.B + b) * T.CH + ch) * side + py) * side + px, v);
 #pragma unroll
-        for (int e = 0; e < VEC; e += 4)
-          __stcs(reinterpret_cast<float4*>(dst + e),
-                 pow2 ? make_float4(__fmul_rn(acc[r][e], rcp), __fmul_rn(acc[r][e + 1], rcp), __fmul_rn(acc[r][e + 2], rcp),
-                                    __fmul_rn(acc[r][e + 3], rcp))
-                      : make_float4(__fdiv_rn(acc[r][e], cnt), __fdiv_rn(acc[r][e + 1], cnt), __fdiv_rn(acc[r][e + 2], cnt),
-                                    __fdiv_rn(acc[r][e + 3], cnt)));
-      } else {
+            for (int e = 0; e < VEC; ++e) {
+              float p = __fadd_rn(__fmul_rn(v[e], 0.5f), 0.5f);
+              p = fminf(fmaxf(p, 0.f), 1.f);
+              acc[e] = __fadd_rn(acc[e], p);                             // image[...] += patch (ed:306)
+            }
+          }
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) dst[e] = pow2 ? __fmul_rn(acc[r][e], rcp) : __fdiv_rn(acc[r][e], cnt);
+        for (int e = 0; e < VEC; ++e) acc[e] = pow2 ? __fmul_rn(acc[e], rcp) : __fdiv_rn(acc[e], cnt);   // image / count
+        store_row(dst0 + (long long)r * Wp, acc);
       }
     }
   }
@@ -112,15 +126,15 @@ extern "C" int ed_tile_blend(const ed_tiles_t* tiles, const void* patches, int p
   const int Wp = T.W * T.scale, Hp = T.H * T.scale;
   const bool al = ((reinterpret_cast<uintptr_t>(image) & 15) == 0) && ((reinterpret_cast<uintptr_t>(patches) & 15) == 0);
   const int vec = (al && T.scale % 8 == 0) ? 8 : (al && T.scale % 4 == 0) ? 4 : 1;
-  const int rows_per = (T.scale % 4 == 0) ? 4 : 1;
+  const int rows_per = (vec == 8) ? 8 : (T.scale % 4 == 0) ? 4 : 1;
   const int cols = Wp / vec, rows = (Hp + rows_per - 1) / rows_per;
   const dim3 block(32, 8);
   const int planes = T.B * T.CH;
   const dim3 g((cols + 31) / 32, (rows + 7) / 8, planes > 65535 ? 65535 : planes);
-#define ED_BLEND(PT)                                                                                 \
-  if (vec == 8) tile_blend_kernel<PT, 8, 4><<<g, block, 0, stream>>>(T, (const PT*)patches, image);    \
-  else if (vec == 4) tile_blend_kernel<PT, 4, 4><<<g, block, 0, stream>>>(T, (const PT*)patches, image); \
-  else if (rows_per == 4) tile_blend_kernel<PT, 1, 4><<<g, block, 0, stream>>>(T, (const PT*)patches, image); \
+#define ED_BLEND(PT)                                                                                          \
+  if (vec == 8 && rows_per == 8) tile_blend_kernel<PT, 8, 8><<<g, block, 0, stream>>>(T, (const PT*)patches, image); \
+  else if (vec == 4) tile_blend_kernel<PT, 4, 4><<<g, block, 0, stream>>>(T, (const PT*)patches, image);          \
+  else if (rows_per >= 4) tile_blend_kernel<PT, 1, 4><<<g, block, 0, stream>>>(T, (const PT*)patches, image);     \
   else tile_blend_kernel<PT, 1, 1><<<g, block, 0, stream>>>(T, (const PT*)patches, image);
   switch (patch_dtype) {
     case ED_F32: ED_BLEND(float) break;

@@ -96,3 +96,54 @@ def _oracle_cuda(m, kw, autocast):
 
         m.unet = NoAutocast()
     return rp.denoise(m, **kw)
+
+
+def test_cuda_graph_and_lookahead_mode_is_bit_identical_to_eager():
+    """use_cuda_graphs replays each wave's UNet forward from static buffers; results must not change."""
+    g = load_golden("xl_1024x2048_T3_R7")
+    outs = []
+    for graphs in (False, True):
+        ed = make_ed(g["sd_version"], g["view_batch_size"], "cuda")
+        ed.rng_device = torch.device("cpu")
+        ed.autocast = False
+        ed.use_cuda_graphs = graphs
+        ed.seed_everything(g["seed"])
+        lat, _ = ed.denoise(**oracle_kwargs(g["kwargs"]), **NOBAR)
+        outs.append(lat.clone())
+    assert torch.equal(outs[0], outs[1])
+    assert torch.mean((outs[1] - g["latent"].cuda()) ** 2).item() < 1e-8
+
+
+def test_bf16_unet_input_path_stays_within_north_star_tolerance():
+    """bench configuration: gather kernels write the UNet batch in bf16 (inputs rounded to bf16, UNet fp32 stub)."""
+    g = load_golden("sd21_512x1024_T4_R4")
+    ed = make_ed(g["sd_version"], g["view_batch_size"], "cuda")
+    ed.rng_device = torch.device("cpu")
+    ed.autocast = False
+    ed.unet_input_dtype = torch.bfloat16
+    ed.unet = ed.unet.to(torch.bfloat16)
+    ed.seed_everything(g["seed"])
+    lat, _ = ed.denoise(**oracle_kwargs(g["kwargs"]), **NOBAR)
+    mse = torch.mean((lat - g["latent"].cuda()) ** 2).item()
+    assert mse < 1e-3, mse            # BASELINE.json north_star tolerance (bf16 rounding of UNet inputs/outputs)
+
+
+@pytest.mark.parametrize("low_vram", [False, True])
+def test_product_tiled_decode_matches_oracle(low_vram):
+    g = load_golden("xl_1080x1920_T2_R2")           # ragged: last tile row / column shifted back -> overlapping tiles
+    ed = make_ed("XL1.0", 4, "cuda")
+    ed.low_vram = low_vram
+    z = g["latent"].cuda()
+    img = ed.tiled_decode(z)
+    m = oracle_models("XL1.0", 4, "cuda")
+    want = rp.decode_tiled(m, z, low_vram=low_vram)
+    assert img.shape == want.shape
+    assert (img - want).abs().max().item() < 1e-5
+
+
+def test_verbose_mode_logs_intermediate_x0_grid():
+    ed = make_ed("2.1", 4, "cuda")
+    ed.verbose, ed.log_freq, ed.autocast = True, 1, False
+    ed.seed_everything(0)
+    imgs, log = ed.generate_image("a", "b", height=512, width=768, num_inference_steps=2, resampling_steps=1, **NOBAR)
+    assert "intermediate_x0_imgs" in log and imgs[0].size == (768, 512)
