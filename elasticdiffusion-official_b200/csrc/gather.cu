@@ -349,8 +349,60 @@ int ed_pad_views(const ed_plan_t* plan, const float* const strips[4], void* canv
   return ED_OK;
 }
 
-// ---- K10a: tile gather ---------------------------------------------------------------------------------------
 }  // extern "C"
+
+// ---- K12: ControlNet condition batch --------------------------------------------------------------------------
+namespace ed {
+template <typename T>
+__global__ void __launch_bounds__(256) gather_cond_kernel(const ed_plan_t P, int R1, const float* __restrict__ cond, int CH,
+                                                          int scale, const int32_t* __restrict__ row_map,
+                                                          const int32_t* __restrict__ col_map,
+                                                          const int32_t* __restrict__ vorigin, T* __restrict__ out) {
+  const int X = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int pW = P.dW * scale, pH = P.dH * scale;
+  if (X >= pW || Y >= pH) return;
+  const int n_global = 2 * P.B * R1, n_all = n_global + P.nv * P.B;
+  const int ch_ = P.lh * scale, cw_ = P.lw * scale;                    // prepared condition size
+  for (int z = blockIdx.z; z < n_all * CH; z += gridDim.z) {
+    const int n = z / CH, c = z - n * CH;
+    float v = 0.f;
+    if (n < n_global) {                                               // zero-padded cond[s] (cn:457-461)
+      const int s = (n / P.B) & 1;
+      const int y = Y - P.g_tp * scale, x = X - P.g_lp * scale;
+      if (y >= 0 && y < ch_ && x >= 0 && x < cw_) v = __ldg(cond + (((long long)s * CH + c) * ch_ + y) * cw_ + x);
+    } else {                                                          // nearest-upsampled cond[0], view box (cn:933-949)
+      const int vi = (n - n_global) / P.B;
+      const int y = Y - P.v_tp * scale, x = X - P.v_lp * scale;
+      if (y >= 0 && y < P.vh * scale && x >= 0 && x < P.vw * scale) {
+        const int sy = __ldg(row_map + __ldg(vorigin + 2 * vi) + y), sx = __ldg(col_map + __ldg(vorigin + 2 * vi + 1) + x);
+        v = __ldg(cond + ((long long)c * ch_ + sy) * cw_ + sx);
+      }
+    }
+    out[((long long)z * pH + Y) * pW + X] = from_f32<T>(v);
+  }
+}
+}  // namespace ed
+
+extern "C" int ed_gather_cond(const ed_plan_t* plan, int R1, const float* cond, int CH, int scale, const int32_t* row_map,
+                              const int32_t* col_map, const int32_t* vorigin, void* out, int out_dtype, void* stream_) {
+  if (!plan || !cond || !row_map || !col_map || !vorigin || !out || R1 <= 0 || CH <= 0 || scale <= 0) return ED_ERR_INVALID;
+  const ed_plan_t& P = *plan;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const dim3 block(32, 8);
+  const long long planes = (long long)(2 * P.B * R1 + P.nv * P.B) * CH;
+  const dim3 grid((P.dW * scale + 31) / 32, (P.dH * scale + 7) / 8, planes > 65535 ? 65535 : (int)planes);
+  switch (out_dtype) {
+    case ED_F32: gather_cond_kernel<float><<<grid, block, 0, stream>>>(P, R1, cond, CH, scale, row_map, col_map, vorigin, (float*)out); break;
+    case ED_F16: gather_cond_kernel<__half><<<grid, block, 0, stream>>>(P, R1, cond, CH, scale, row_map, col_map, vorigin, (__half*)out); break;
+    case ED_BF16: gather_cond_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(P, R1, cond, CH, scale, row_map, col_map, vorigin, (__nv_bfloat16*)out); break;
+    default: return ED_ERR_INVALID;
+  }
+  ED_LAUNCH_CHECK();
+  return ED_OK;
+}
+
+// ---- K10a: tile gather ---------------------------------------------------------------------------------------
 
 namespace ed {
 __global__ void __launch_bounds__(256) tile_gather_generic(const float* __restrict__ latent, int B, int C, int H, int W,

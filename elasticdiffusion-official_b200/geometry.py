@@ -245,3 +245,23 @@ def build_tiles(H, W, sample_size, scale, low_vram=False) -> TileGeometry:
     tcf, tcc = cover_ranges([wins[c][2] for c in range(ntc)], core, W)
     return TileGeometry(wins, ntr, ntc, core, pad, stride,
                         dict(tiles=flat, trow_first=trf, trow_cnt=trc, tcol_first=tcf, tcol_cnt=tcc))
+
+
+def cond_geometry(geo: WaveGeometry, scale, window, context):
+    """Index tables of the ControlNet condition batch (reference elastic_diffusion_w_controlnet.py "cn:N"):
+    nearest-upsample maps from the prepared condition (lh*scale, lw*scale) to full pixel size (cn:933) and the pixel
+    origin of every view's context box computed with the window coordinates x scale and n = context*scale//2
+    (cn:946-949; the reference hard-codes 8)."""
+    H, W = geo.H, geo.W
+    row_map = nearest_index(geo.lh * scale, H * scale)
+    col_map = nearest_index(geo.lw * scale, W * scale)
+    n = (context * scale) // 2
+    origin = []
+    for (h0, h1, w0, w1) in geo.views:
+        n_t, n_b = context_extent(h0 * scale, h1 * scale, n, H * scale)
+        n_l, n_r = context_extent(w0 * scale, w1 * scale, n, W * scale)
+        if ((h1 - h0) * scale + n_t + n_b, (w1 - w0) * scale + n_l + n_r) != (geo.vh * scale, geo.vw * scale):
+            raise ValueError("condition view and latent view sizes disagree (odd context size): the reference's ControlNet "
+                             "call fails on this configuration too")
+        origin += [h0 * scale - n_t, w0 * scale - n_l]
+    return row_map, col_map, origin

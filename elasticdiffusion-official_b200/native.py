@@ -63,6 +63,8 @@ EXPORTS = {
     "ed_wave_epilogue": (C.c_int, [C.POINTER(Plan), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ed_renoise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "ed_gather_cond": (C.c_int, [C.POINTER(Plan), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_int, C.c_void_p]),
     "ed_tile_gather": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                  C.c_int, C.c_void_p, C.c_void_p]),
     "ed_tile_blend": (C.c_int, [C.POINTER(Tiles), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),

@@ -27,7 +27,7 @@ import torch.nn as nn
 
 from . import native
 from .ddim import DDIMSchedule, check_scheduler, renoise_scalars, step_scalars
-from .geometry import build_geometry, build_tiles, low_res_size, pad_split
+from .geometry import build_geometry, build_tiles, cond_geometry, low_res_size, pad_split
 
 try:  # progress bar default of the reference signature (ed:963)
     from tqdm import tqdm
@@ -326,6 +326,7 @@ class ElasticDiffusion(nn.Module):
         self.last_run = {}            # counters of the last generate_image call (kernel launches, UNet calls ...)
         self._text_embeds_fn = None
         self._projection_dim = None
+        self.controlnet = None        # set by the ControlNet twin (controlnet.py)
 
     def _finish_init(self):
         for p in self.vae.parameters():                                            # ed:154,173-175
@@ -336,7 +337,8 @@ class ElasticDiffusion(nn.Module):
 
     @classmethod
     def from_components(cls, device, unet, vae, scheduler=None, text_embeds_fn=None, sd_version='2.1',
-                        verbose=False, log_freq=5, view_batch_size=1, low_vram=False, projection_dim=None):
+                        verbose=False, log_freq=5, view_batch_size=1, low_vram=False, projection_dim=None,
+                        controlnet=None, controlnet_model='canny'):
         """Build from already-instantiated modules (what `__init__` gets from `from_pretrained`, ed:144-153).
         `text_embeds_fn(prompts) -> (text_embeddings, pooled)` replaces the CLIP encoders (ed:255-265)."""
         self = cls.__new__(cls)
@@ -347,6 +349,7 @@ class ElasticDiffusion(nn.Module):
         self._text_embeds_fn = text_embeds_fn
         self._projection_dim = projection_dim
         self.tokenizer, self.text_encoder = [], []
+        self.controlnet, self.controlnet_model = controlnet, controlnet_model
         self._finish_init()
         return self
 
@@ -510,7 +513,7 @@ class ElasticDiffusion(nn.Module):
         ent[0].replay()
         return ent[1]
 
-    def _unet(self, canvas, t, text, pooled, time_ids):
+    def _unet(self, canvas, t, text, pooled, time_ids, cond=None, cond_scale=1.0):
         """One batched UNet evaluation of a wave (dense part, through PyTorch; ed:417-426 for the XL kwargs).
         With torch.distributed initialised the samples are sharded over ranks and all-gathered (multi-GPU)."""
         grp, rank, ws = self._dist()
@@ -530,7 +533,13 @@ class ElasticDiffusion(nn.Module):
 
             def call(s=s, e=e, kw=kw):
                 with torch.autocast("cuda", enabled=self.autocast):
-                    return self.unet(canvas[s:e], t, encoder_hidden_states=text[s:e], **kw)["sample"]
+                    res = {}
+                    if cond is not None:   # ControlNet forward feeding residuals into the UNet (cn:482-496, 506-518)
+                        down, mid = self.controlnet(canvas[s:e], t, encoder_hidden_states=text[s:e],
+                                                    controlnet_cond=cond[s:e], conditioning_scale=cond_scale,
+                                                    guess_mode=False, return_dict=False, **kw)
+                        res = {"down_block_additional_residuals": down, "mid_block_additional_residual": mid}
+                    return self.unet(canvas[s:e], t, encoder_hidden_states=text[s:e], **kw, **res)["sample"]
             if self.use_cuda_graphs:
                 outs.append(self._graphed(("unet", canvas.data_ptr(), text.data_ptr(), s, e), call))
             else:
@@ -594,8 +603,9 @@ class ElasticDiffusion(nn.Module):
     def denoise(self, prompts, negative_prompts='', height=768, width=768, num_inference_steps=50,
                 guidance_scale=10.0, resampling_steps=20, new_p=0.3, rrg_stop_t=0.2, rrg_init_weight=1000,
                 rrg_scherduler_cls=CosineScheduler, cosine_scale=3.0, repaint_sampling=True, progress=tqdm,
-                step_callback=None, max_steps=None):
-        """The loop of ed:967-1078.  Returns (final latent (B,4,H/8,W/8) fp32 on device, image_log)."""
+                step_callback=None, max_steps=None, condition_image=None, controlnet_conditioning_scale=1.0):
+        """The loop of ed:967-1078.  Returns (final latent (B,4,H/8,W/8) fp32 on device, image_log).
+        `condition_image`: prepared ControlNet condition (1,3,ds_h*8,ds_w*8) float tensor (ControlNet twin, cn:1119-1322)."""
         self._require_cuda()
         L = native.lib()
         sf = self.vae_scale_factor
@@ -677,6 +687,32 @@ class ElasticDiffusion(nn.Module):
         rrg_norm = float(torch.tensor(2.0 / (C * H * W), dtype=torch.float64).to(torch.float32))
         image_log = {}
 
+        # ---- ControlNet condition batches (static for the whole call): one K12 launch per wave shape ----------------------
+        cond1 = cond2 = None
+        if condition_image is not None:
+            if self.controlnet is None:
+                raise ValueError("condition_image given but no ControlNet is loaded (use the elastic_diffusion_w_controlnet class)")
+            if B != 1:
+                raise ValueError("the ControlNet twin prepares the condition with batch_size=1 (cn:1187): one prompt per call")
+            img = condition_image.to(device=dev, dtype=torch.float32)
+            if tuple(img.shape) != (1, 3, ds[0] * sf, ds[1] * sf):
+                raise ValueError(f"condition image must be (1, 3, {ds[0] * sf}, {ds[1] * sf}), got {tuple(img.shape)}")
+            cdt = next(self.controlnet.parameters()).dtype
+            prepared = torch.cat([img.to(cdt)] * 2).float().contiguous()                       # cn:1028-1031 (CFG doubling)
+            row_map, col_map, origin = cond_geometry(geo, sf, vc["window_size"], vc["context_size"])
+            ctabs = [_i32(dev, v) for v in (row_map, col_map, origin)]
+            cond_dtype = self.unet_input_dtype or torch.float32
+
+            def build_cond(R1):
+                out_c = torch.empty(2 * B * R1 + nv * B, 3, native_size * sf, native_size * sf, device=dev, dtype=cond_dtype)
+                native.check(L.ed_gather_cond(ctypes.byref(plan), R1, native.ptr(prepared), 3, sf, native.ptr(ctabs[0]),
+                                              native.ptr(ctabs[1]), native.ptr(ctabs[2]), native.ptr(out_c),
+                                              native.dtype_code(cond_dtype), native.stream_handle()), "ed_gather_cond")
+                self.last_run["kernel_launches"] += 1
+                return out_c
+            cond1 = build_cond(R + 1)
+            cond2 = cond1 if R == 0 else build_cond(1)
+
         def launch(name, fn, *args):
             """one libelastic_b200 kernel launch (+ optional CUDA-event bracket on the launching stream)"""
             if self.profile_kernels:
@@ -704,7 +740,8 @@ class ElasticDiffusion(nn.Module):
             if any(s is not None for s in strips_v):
                 launch("ed_pad_views", L.ed_pad_views, ctypes.byref(plan), native.strips_array(strips_v), native.ptr(cv),
                        native.dtype_code(cv.dtype), 2 * B * R1, st)
-            out = self._unet(cv, t_dev, text[:n], pool[:n], None if time_ids is None else time_ids[:n])
+            out = self._unet(cv, t_dev, text[:n], pool[:n], None if time_ids is None else time_ids[:n],
+                             cond1 if R1 == R + 1 else cond2, controlnet_conditioning_scale)
             if out.dtype == torch.float16:
                 prm.flags |= native.FLAG_FP16_SEM
             native.check(L.ed_upload_step_params(native.ptr(d_params[slot]), ctypes.byref(prm), st), "upload")

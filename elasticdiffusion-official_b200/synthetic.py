@@ -96,10 +96,49 @@ class StubUNet(nn.Module):
             add = torch.cat([feats, added_cond_kwargs["text_embeds"].to(x.dtype)], dim=-1)
             emb = emb + self.add_embedding.linear_1(add)
         h = self.conv_in(x) + emb[:, :, None, None]
+        # ControlNet residuals (reference elastic_diffusion_w_controlnet.py:493-496): added to the hidden state
+        down = kw.get("down_block_additional_residuals")
+        mid = kw.get("mid_block_additional_residual")
+        if down is not None:
+            for r in down:
+                h = h + r.to(h.dtype)
+        if mid is not None:
+            h = h + mid.to(h.dtype)
         h = F.silu(h)
         # denoiser-like: mostly "the noise is what you see" plus a conditioned non-linear term, so that the
         # sampled trajectory stays O(1) over 50 DDIM steps (a pure random conv makes latents grow ~1/sqrt(abar_T))
         return {"sample": 0.95 * x + 0.2 * self.conv_out(h)}
+
+
+class StubControlNet(nn.Module):
+    """Tiny ControlNet with the call contract the reference uses (elastic_diffusion_w_controlnet.py:482-491):
+    `controlnet(x, t, encoder_hidden_states=..., controlnet_cond=..., conditioning_scale=..., guess_mode=False,
+    return_dict=False[, added_cond_kwargs=...]) -> (down_block_res_samples, mid_block_res_sample)`.
+    The condition image lives at pixel resolution (8x the latent); a stride-8 conv brings it to the latent grid."""
+
+    def __init__(self, hidden=16, cross_dim=16, seed=99):
+        super().__init__()
+        self.cond_in = nn.Conv2d(3, hidden, 8, stride=8)
+        self.x_in = nn.Conv2d(4, hidden, 3, padding=1)
+        self.text_proj = nn.Linear(cross_dim, hidden)
+        self.mid = nn.Conv2d(hidden, hidden, 3, padding=1)
+        _seeded_(self, seed, scale=0.7)
+
+    @property
+    def dtype(self):
+        return self.cond_in.weight.dtype
+
+    def forward(self, x, t, encoder_hidden_states=None, controlnet_cond=None, conditioning_scale=1.0, guess_mode=False,
+                return_dict=False, added_cond_kwargs=None):
+        b = x.shape[0]
+        t = torch.as_tensor(t, device=x.device).reshape(-1)
+        if t.numel() == 1:
+            t = t.expand(b)
+        emb = self.text_proj(encoder_hidden_states.to(x.dtype).mean(dim=1)) + timestep_embedding(t, 16).to(x.dtype)
+        h = F.silu(self.x_in(x) + self.cond_in(controlnet_cond.to(x.dtype)) + emb[:, :, None, None])
+        down = [h * conditioning_scale]
+        mid = torch.tanh(self.mid(h)) * conditioning_scale
+        return down, mid
 
 
 class _LatentDist:

@@ -157,6 +157,18 @@ int ed_wave_epilogue(const ed_plan_t* plan, const ed_step_params_t* d_params, co
 int ed_renoise(const ed_step_params_t* d_params, const float* x, const float* noise, float* out,
                int64_t numel, void* stream);
 
+/* ---- K12: ControlNet condition batch of a wave (elastic_diffusion_w_controlnet.py, "cn:N") ---------------------------
+ * Replaces F.pad of the condition for padded global passes (cn:457-461) and, for the local views, the nearest upsample
+ * of condition_image[0:1] to full pixel size + crop_with_context at 8x coordinates + cat (cn:933, 946-949, 959-961).
+ * The condition never changes during a call, so this runs ONCE per wave shape, not per step.
+ *   cond     (2, CH, ch, cw) fp32 : prepared, CFG-doubled condition image, ch = lh*scale, cw = lw*scale (cn:1183-1193)
+ *   row_map  [H*scale], col_map [W*scale] : source row / col of the nearest upsample to (H*scale, W*scale)
+ *   vorigin  [nv*2] : pixel origin (row, col) of every view's context box in the upsampled image
+ *   out      (2*B*R1 + nv*B, CH, dH*scale, dW*scale) of out_dtype: sample (k,s,b) = zero-padded cond[s];
+ *            sample (view v, b) = upsampled cond[0] box, zero-padded when the view is smaller than native */
+int ed_gather_cond(const ed_plan_t* plan, int R1, const float* cond, int CH, int scale, const int32_t* row_map,
+                   const int32_t* col_map, const int32_t* vorigin, void* out, int out_dtype, void* stream);
+
 /* ---- K10: tiled decode glue -- replaces F.pad + per-tile slicing/cat (ed:287-300) and the accumulate /
  * count / divide blend (ed:303-308) -----------------------------------------------------------------------------
  * Tile table (DEVICE int32): tiles[j*4 .. j*4+3] = h0,h1,w0,w1 of core tile j in latent units, row-major tile grid

@@ -45,8 +45,25 @@ def load_reference_module(name="elastic_diffusion"):
         setattr(d, n, type(n, (), {}))
     for n in ("AttnProcessor2_0", "LoRAAttnProcessor2_0", "LoRAXFormersAttnProcessor", "XFormersAttnProcessor"):
         setattr(da, n, type(n, (), {}))
+    setattr(dm, "ControlNetModel", d.ControlNetModel)
+    dip = types.ModuleType("diffusers.image_processor")
+
+    class VaeImageProcessor:   # only `preprocess` is used (cn:1017); tensors pass through, sizes are checked
+        def __init__(self, **kw):
+            pass
+
+        def preprocess(self, image, height=None, width=None):
+            assert torch.is_tensor(image) and image.shape[-2:] == (height, width), "shim: pass a (1,3,h,w) tensor"
+            return image
+    dip.VaeImageProcessor = VaeImageProcessor
     if "diffusers" not in sys.modules:
-        sys.modules.update({"diffusers": d, "diffusers.models": dm, "diffusers.models.attention_processor": da})
+        sys.modules.update({"diffusers": d, "diffusers.models": dm, "diffusers.models.attention_processor": da,
+                            "diffusers.image_processor": dip})
+    if "cv2" not in sys.modules:            # only used by process_condition_image (canny), outside the hot path
+        try:
+            import cv2  # noqa: F401
+        except Exception:
+            sys.modules["cv2"] = types.ModuleType("cv2")
     path = os.path.join(reference_dir(), name + ".py")
     spec = importlib.util.spec_from_file_location("_ref_" + name, path)
     mod = importlib.util.module_from_spec(spec)
@@ -56,9 +73,10 @@ def load_reference_module(name="elastic_diffusion"):
 
 
 def build_reference(unet, vae, scheduler, text_fn, sd_version="2.1", device="cpu", view_batch_size=1,
-                    verbose=False, low_vram=False, projection_dim=None):
-    """Reference `ElasticDiffusion` instance with injected components (bypasses `from_pretrained`)."""
-    ref = load_reference_module()
+                    verbose=False, low_vram=False, projection_dim=None, controlnet=None):
+    """Reference `ElasticDiffusion` instance with injected components (bypasses `from_pretrained`).
+    With `controlnet` the class comes from the unmodified elastic_diffusion_w_controlnet.py."""
+    ref = load_reference_module("elastic_diffusion_w_controlnet" if controlnet is not None else "elastic_diffusion")
     o = ref.ElasticDiffusion.__new__(ref.ElasticDiffusion)
     nn.Module.__init__(o)
     o.device = torch.device(device)
@@ -69,6 +87,9 @@ def build_reference(unet, vae, scheduler, text_fn, sd_version="2.1", device="cpu
     o.log_freq = 5
     o.low_vram = low_vram
     o.unet, o.vae, o.scheduler = unet, vae, scheduler
+    if controlnet is not None:
+        o.controlnet, o.controlnet_model = controlnet, "canny"
+        o.control_image_processor = sys.modules["diffusers.image_processor"].VaeImageProcessor()
     o.vae_scale_factor = 2 ** (len(vae.config.block_out_channels) - 1)
     o.get_text_embeds = text_fn
     if projection_dim is not None:

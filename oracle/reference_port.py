@@ -230,8 +230,9 @@ class Models:
     """The injected dense modules + the few attributes the hot path reads from `self` (ed:111-163)."""
 
     def __init__(self, unet, vae, scheduler, text_fn, sd_version, device="cpu", view_batch_size=1,
-                 patch_size=None, projection_dim=None, dtype=torch.float32):
+                 patch_size=None, projection_dim=None, dtype=torch.float32, controlnet=None):
         self.unet, self.vae, self.scheduler, self.text_fn = unet, vae, scheduler, text_fn
+        self.controlnet = controlnet          # ControlNet twin: elastic_diffusion_w_controlnet.py ("cn:N")
         self.sd_version, self.device, self.view_batch_size = sd_version, torch.device(device), view_batch_size
         self.dtype = dtype
         self.scale = 2 ** (len(vae.config.block_out_channels) - 1)                     # ed:156
@@ -258,8 +259,10 @@ def background_strip(m: Models, size, t, tag):
     return z_t
 
 
-def unet_call(m: Models, x, t, text, pooled):
-    """ed:393-432 (`unet_step`): pad to the native size with background strips, UNet, crop."""
+def unet_call(m: Models, x, t, text, pooled, cond=None, cond_scale=1.0):
+    """ed:393-432 (`unet_step`): pad to the native size with background strips, UNet, crop.
+    ControlNet twin cn:434-524: the condition image is zero-padded by pad*vae_scale (cn:457-461), a ControlNet forward on
+    the padded latent yields residuals that are fed to the UNet (cn:482-496 / 506-518)."""
     native = 128 if m.sd_version.startswith("XL") else 64                               # ed:398-400
     x = m.scheduler.scale_model_input(x, t)
     hp, wp = max(native - x.shape[-2], 0), max(native - x.shape[-1], 0)
@@ -275,6 +278,18 @@ def unet_call(m: Models, x, t, text, pooled):
             s1 = background_strip(m, sb, t, f"{dim}_1").repeat(B, 1, 1, 1).to(x)
             s2 = background_strip(m, sa, t, f"{dim}_2").repeat(B, 1, 1, 1).to(x)
             xin = torch.cat([s1, xin, s2], dim=dim)
+        if cond is not None:
+            sc = m.scale
+            cond = F.pad(cond, (lp * sc, rp * sc, tp * sc, bp * sc))                     # cn:457-461
+    extra = {}
+
+    def control(added=None):
+        if cond is None:
+            return {}
+        kw = {} if added is None else {"added_cond_kwargs": added}
+        down, mid = m.controlnet(xin, t, encoder_hidden_states=text, controlnet_cond=cond[:xin.shape[0]],
+                                 conditioning_scale=cond_scale, guess_mode=False, return_dict=False, **kw)   # cn:482-491
+        return {"down_block_additional_residuals": down, "mid_block_additional_residual": mid}
     if m.sd_version.startswith("XL"):
         ids = list(m.default_size + (0, 0) + m.default_size)                            # ed:233, 414
         n_expected = m.unet.add_embedding.linear_1.in_features
@@ -283,17 +298,19 @@ def unet_call(m: Models, x, t, text, pooled):
             raise ValueError(f"Model expects an added time embedding vector of length {n_expected}, but a vector of "
                              f"{n_passed} was created.")
         time_ids = torch.tensor([ids], dtype=text.dtype).to(m.device).repeat(xin.shape[0], 1)
-        out = m.unet(xin, t, encoder_hidden_states=text,
-                     added_cond_kwargs={"text_embeds": pooled, "time_ids": time_ids})["sample"]
+        added = {"text_embeds": pooled, "time_ids": time_ids}
+        out = m.unet(xin, t, encoder_hidden_states=text, added_cond_kwargs=added, **control(added))["sample"]
     else:
-        out = m.unet(xin, t, encoder_hidden_states=text)["sample"]
+        out = m.unet(xin, t, encoder_hidden_states=text, **control())["sample"]
     if hp > 0 or wp > 0:
         out = out[:, :, tp:out.shape[-2] - bp, lp:out.shape[-1] - rp]                    # ed:429-430
     return out
 
 
-def global_direction(m: Models, latent, t, text, pooled, tabs: ResampleTables, resampling_steps, drop_p, trace=None):
-    """ed:650-690 (`approximate_latent_direction_w_resampling`)."""
+def global_direction(m: Models, latent, t, text, pooled, tabs: ResampleTables, resampling_steps, drop_p, trace=None,
+                     cimg=None, cond_scale=1.0):
+    """ed:650-690 (`approximate_latent_direction_w_resampling`); the ControlNet twin threads the (CFG-doubled) condition
+    image through to unet_step (cn:527-537, 744-781)."""
     target = torch.full_like(latent, float("nan")).half()                               # ed:655 (fp16 on purpose)
     exclude, prev = None, None
     info = {"init_downsampled_latent": None}
@@ -312,7 +329,7 @@ def global_direction(m: Models, latent, t, text, pooled, tabs: ResampleTables, r
         exclude[torch.arange(n_cells), prev] = True                                      # ed:675
         if info["init_downsampled_latent"] is None:
             info["init_downsampled_latent"] = low.clone()
-        both = unet_call(m, torch.cat([low] * 2), t, text, pooled)                       # ed:436-438
+        both = unet_call(m, torch.cat([low] * 2), t, text, pooled, cimg, cond_scale)     # ed:436-438
         uncond, cond = both.chunk(2)
         direction = cond - uncond                                                        # ed:440
         up = nearest_resize(direction, (target.size(2), target.size(3)))                 # ed:636
@@ -328,9 +345,14 @@ def global_direction(m: Models, latent, t, text, pooled, tabs: ResampleTables, r
     return target, info
 
 
-def local_uncond(m: Models, latent, t, uncond_text, uncond_pooled):
-    """ed:814-864 (`compute_local_uncond_signal`): view gather -> UNet -> first-writer-wins scatter."""
+def local_uncond(m: Models, latent, t, uncond_text, uncond_pooled, cond=None, cond_scale=1.0):
+    """ed:814-864 (`compute_local_uncond_signal`): view gather -> UNet -> first-writer-wins scatter.
+    ControlNet twin cn:917-983: condition_image[0:1] is nearest-upsampled to the full pixel size (cn:933) and cropped per
+    view with the window coordinates x 8 and context*8//2 (cn:946-949, the factor 8 is hard-coded)."""
     H, W = latent.shape[-2:]
+    cond_up = None
+    if cond is not None:
+        cond_up = nearest_resize(cond[0:1], (H * m.scale, W * m.scale))
     vc = m.view_config
     h_ws = H if vc["window_size"] + vc["context_size"] >= H else vc["window_size"]        # ed:820-825
     w_ws = W if vc["window_size"] + vc["context_size"] >= W else vc["window_size"]
@@ -341,7 +363,12 @@ def local_uncond(m: Models, latent, t, uncond_text, uncond_pooled):
         chunk = views[s:s + m.view_batch_size]
         boxes = [context_box(v, n, H, W) for v in chunk]
         crops = torch.cat([latent[:, :, r0:r1, c0:c1] for (r0, r1, c0, c1), _ in boxes])
-        pred = unet_call(m, crops, t, torch.cat([uncond_text] * len(chunk)), torch.cat([uncond_pooled] * len(chunk)))
+        cviews = None
+        if cond_up is not None:
+            cb = [context_box(tuple(8 * q for q in v), (vc["context_size"] * 8) // 2, H * 8, W * 8)[0] for v in chunk]
+            cviews = torch.cat([cond_up[:, :, r0:r1, c0:c1] for (r0, r1, c0, c1) in cb])
+        pred = unet_call(m, crops, t, torch.cat([uncond_text] * len(chunk)), torch.cat([uncond_pooled] * len(chunk)),
+                         cviews, cond_scale)
         for (h0, h1, w0, w1), (_, (n_t, n_b, n_l, n_r)), p in zip(chunk, boxes, pred.chunk(len(chunk))):
             centre = p[:, :, n_t:p.shape[-2] - n_b, n_l:p.shape[-1] - n_r]
             dst = out[:, :, h0:h1, w0:w1]
@@ -407,8 +434,10 @@ class ConstWeight(LinearWeight):
 @torch.no_grad()
 def denoise(m: Models, prompts, negative_prompts="", height=768, width=768, num_inference_steps=50,
             guidance_scale=10.0, resampling_steps=20, new_p=0.3, rrg_stop_t=0.2, rrg_init_weight=1000,
-            rrg_scheduler="cosine", cosine_scale=3.0, repaint_sampling=True, trace=None, step_callback=None):
-    """The loop of ed:952-1078; returns the final latent (what the reference hands to the VAE at ed:1121)."""
+            rrg_scheduler="cosine", cosine_scale=3.0, repaint_sampling=True, trace=None, step_callback=None,
+            condition_image=None, controlnet_conditioning_scale=1.0):
+    """The loop of ed:952-1078; returns the final latent (what the reference hands to the VAE at ed:1121).
+    With `condition_image` ((1,3,ds_h*8,ds_w*8) float tensor in [0,1]) it is the ControlNet twin's loop cn:1119-1322."""
     ds = downsample_size(height, width, m.sd_version, m.scale)                             # ed:968
     m.default_size = (4 * height, 4 * width)                                               # ed:969
     steps_rrg = num_inference_steps - int(num_inference_steps * rrg_stop_t)
@@ -428,17 +457,23 @@ def denoise(m: Models, prompts, negative_prompts="", height=768, width=768, num_
     m.scheduler.set_timesteps(num_inference_steps)
     ts = m.scheduler.timesteps
     tabs = ResampleTables(x.shape[-2], x.shape[-1], ds)
+    cond, cs = None, controlnet_conditioning_scale
+    if condition_image is not None:                                                        # prepare_image, cn:1005-1033, 1183-1193
+        img = condition_image.to(dtype=torch.float32)
+        assert img.shape[-2:] == (ds[0] * m.scale, ds[1] * m.scale), "condition image must be (ds_h*8, ds_w*8)"
+        img = img.repeat_interleave(1, dim=0).to(device=m.device, dtype=m.controlnet.dtype)
+        cond = torch.cat([img] * 2).to(m.device)                                           # do_classifier_free_guidance
     with torch.autocast("cuda", enabled=(m.device.type == "cuda")):                        # ed:1012
         for i, t in enumerate(ts):
-            d, info = global_direction(m, x, t, text, pooled, tabs, resampling_steps, 1 - new_p, trace)
-            u = local_uncond(m, x, t, un_text, un_pool)
+            d, info = global_direction(m, x, t, text, pooled, tabs, resampling_steps, 1 - new_p, trace, cond, cs)
+            u = local_uncond(m, x, t, un_text, un_pool, cond, cs)
             out = m.scheduler.step(u + guidance_scale * d, t, x)                            # ed:1031-1033
             x0, nxt, cfg = out["pred_original_sample"], out["prev_sample"], guidance_scale
             if repaint_sampling and resampling_steps > 0 and i < len(ts) - 1:               # ed:1038
                 x = renoise(m, nxt, ts[i + 1])
                 cfg = guidance_scale / 3
-                d, info = global_direction(m, x, t, text, pooled, tabs, 0, 1 - new_p)
-                u = local_uncond(m, x, t, un_text, un_pool)
+                d, info = global_direction(m, x, t, text, pooled, tabs, 0, 1 - new_p, None, cond, cs)
+                u = local_uncond(m, x, t, un_text, un_pool, cond, cs)
                 out = m.scheduler.step(u + cfg * d, t, x)
                 x0, nxt = out["pred_original_sample"], out["prev_sample"]
             cascade = torch.zeros_like(nxt)

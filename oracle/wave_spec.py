@@ -171,6 +171,27 @@ def spec_epilogue(geo, prm, latent, unet_out, idx, noise=None):
     return res, x0
 
 
+def spec_gather_cond(geo, R1, cond, scale, row_map, col_map, origin):
+    """ed_gather_cond: (2*B*R1 + nv*B, CH, dH*scale, dW*scale) condition batch (cn:457-461, 933-949)."""
+    import torch.nn.functional as F
+    dev = cond.device
+    B = geo.B
+    lp, rp, tp, bp = geo.g_pad
+    vlp, vrp, vtp, vbp = geo.v_pad
+    s = scale
+    padded = F.pad(cond, (lp * s, rp * s, tp * s, bp * s))                       # (2, CH, dH*s, dW*s)
+    glob = torch.cat([padded[sidx:sidx + 1].expand(B, -1, -1, -1) for _ in range(R1) for sidx in (0, 1)])
+    rm, cm = torch.tensor(row_map, device=dev), torch.tensor(col_map, device=dev)
+    up = cond[0:1][:, :, rm][:, :, :, cm]                                         # nearest upsample to full pixel size
+    views = []
+    for v in range(geo.nv):
+        r0, c0 = origin[2 * v], origin[2 * v + 1]
+        box = up[:, :, r0:r0 + geo.vh * s, c0:c0 + geo.vw * s]
+        box = F.pad(box, (vlp * s, vrp * s, vtp * s, vbp * s))
+        views.append(box.expand(B, -1, -1, -1))
+    return torch.cat([glob] + views)
+
+
 def spec_tile_gather(latent, tiles, core, pad):
     import torch.nn.functional as F
     zp = F.pad(latent, (pad, pad, pad, pad), "constant", 0)
@@ -192,12 +213,13 @@ def spec_tile_blend(patches, tiles, B, H, W, core, pad, scale):
 @torch.no_grad()
 def denoise_wave_form(ed, prompts, negative_prompts="", height=768, width=768, num_inference_steps=50,
                       guidance_scale=10.0, resampling_steps=20, new_p=0.3, rrg_stop_t=0.2, rrg_init_weight=1000,
-                      cosine_scale=3.0, repaint_sampling=True, trace=None):
+                      cosine_scale=3.0, repaint_sampling=True, trace=None, condition_image=None,
+                      controlnet_conditioning_scale=1.0):
     """The product's wave-batched loop (pipeline.ElasticDiffusion.denoise) with the CUDA ops replaced by the spec
     emulations above; uses the product's geometry, RngLedger and DDIM scalar helpers unchanged."""
     import importlib
     pkg = importlib.import_module(type(ed).__module__.rsplit(".", 1)[0])
-    pl = importlib.import_module(type(ed).__module__)
+    pl = importlib.import_module(pkg.__name__ + ".pipeline")
     from_ddim = importlib.import_module(pkg.__name__ + ".ddim")
     sf = ed.vae_scale_factor
     ds = ed.get_downsample_size(height, width)
@@ -223,13 +245,25 @@ def denoise_wave_form(ed, prompts, negative_prompts="", height=768, width=768, n
     time_ids = ed._get_add_time_ids(ed.default_size, (0, 0), ed.default_size, dtype=text_pair.dtype) if is_xl else None
     rrg_norm = float(torch.tensor(2.0 / (C * H * W), dtype=torch.float64).to(torch.float32))
 
+    conds = {}
+    if condition_image is not None:
+        prepared = torch.cat([condition_image.float()] * 2)
+        rm, cm, org = pkg.geometry.cond_geometry(geo, sf, vc["window_size"], vc["context_size"])
+        conds = {R1: spec_gather_cond(geo, R1, prepared, sf, rm, cm, org) for R1 in {resampling_steps + 1, 1}}
+
     def unet(canvas, t, R1):
         text = torch.cat([text_pair] * R1 + [un_text] * nv)
         pool = torch.cat([pool_pair] * R1 + [un_pool] * nv)
         kw = {}
         if is_xl:
             kw["added_cond_kwargs"] = {"text_embeds": pool, "time_ids": time_ids.to(canvas.device).repeat(len(canvas), 1)}
-        return ed.unet(canvas, t, encoder_hidden_states=text, **kw)["sample"]
+        res = {}
+        if conds:
+            down, mid = ed.controlnet(canvas, t, encoder_hidden_states=text, controlnet_cond=conds[R1],
+                                      conditioning_scale=controlnet_conditioning_scale, guess_mode=False,
+                                      return_dict=False, **kw)
+            res = {"down_block_additional_residuals": down, "mid_block_additional_residual": mid}
+        return ed.unet(canvas, t, encoder_hidden_states=text, **kw, **res)["sample"]
 
     def wave(x_in, t, idx, R1, sg, sv, prm, noise):
         canvas = torch.cat([spec_pick_gather(geo, R1, x_in, idx, sg), spec_gather_views(geo, x_in, sv)])

@@ -32,6 +32,16 @@ CASES = {
     "xl_1536x1536_T2_R3": ("XL1.0", 16, dict(height=1536, width=1536, num_inference_steps=2, resampling_steps=3)),
     "xl_1080x1920_T2_R2": ("XL1.0", 4, dict(height=1080, width=1920, num_inference_steps=2, resampling_steps=2)),
 }
+# ControlNet twin (elastic_diffusion_w_controlnet.py): condition = fixed-seed uniform image of the prepared size
+CN_CASES = {
+    "cn_sd21_512x1024_T3_R3": ("2.1", 8, dict(height=512, width=1024, num_inference_steps=3, resampling_steps=3,
+                                              controlnet_conditioning_scale=0.8)),
+    "cn_xl_1024x2048_T2_R2": ("XL1.0", 16, dict(height=1024, width=2048, num_inference_steps=2, resampling_steps=2,
+                                                controlnet_conditioning_scale=1.0)),
+    "cn_xl_1080x1920_T2_R1": ("XL1.0", 4, dict(height=1080, width=1920, num_inference_steps=2, resampling_steps=1,
+                                               controlnet_conditioning_scale=0.5)),
+}
+COND_SEED = 7
 DEFAULTS = dict(prompts="a cat", negative_prompts="blurry", guidance_scale=10.0, new_p=0.3, rrg_stop_t=0.2,
                 rrg_init_weight=1000, cosine_scale=10, repaint_sampling=True)
 SEED = 0
@@ -66,5 +76,31 @@ def main():
         print(f"{name}: latent {tuple(latent.shape)} std {latent.std():.4f} images {len(imgs)} x {imgs[0].size}")
 
 
+def condition_for(o_or_ds, seed=COND_SEED):
+    ds = o_or_ds
+    return torch.rand(1, 3, ds[0] * 8, ds[1] * 8, generator=torch.Generator().manual_seed(seed))
+
+
+def main_cn():
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    for name, (sd, vb, kw) in CN_CASES.items():
+        unet, vae, txt, proj = components(sd)
+        cn = syn.StubControlNet()
+        o = build_reference(unet, vae, DDIMRestated(), txt, sd_version=sd, view_batch_size=vb, projection_dim=proj,
+                            controlnet=cn)
+        o.seed_everything(SEED)
+        args = dict(DEFAULTS)
+        args.update(kw)
+        cond = condition_for(o.get_downsample_size(args["height"], args["width"]))
+        imgs, _, latent = run_reference(o, progress=lambda it: it, condition_image=cond, **args)
+        torch.save(dict(sd_version=sd, view_batch_size=vb, seed=SEED, kwargs=args, latent=latent.clone(), cond_seed=COND_SEED,
+                        image_stats=torch.stack([image_stats(i) for i in imgs]), image_size=imgs[0].size),
+                   os.path.join(out_dir, name + ".pt"))
+        print(f"{name}: latent {tuple(latent.shape)} std {latent.std():.4f}")
+
+
 if __name__ == "__main__":
+    if "--cn-only" in sys.argv:
+        main_cn()
+        sys.exit(0)
     main()

@@ -33,7 +33,19 @@ def pytest_collection_modifyitems(config, items):
 
 
 def golden_names():
-    return sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.pt")))
+    return sorted(n for n in (os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.pt")))
+                  if not n.startswith("cn_"))
+
+
+def cn_golden_names():
+    """Goldens of the ControlNet twin (unmodified elastic_diffusion_w_controlnet.py)."""
+    return sorted(n for n in (os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN_DIR, "cn_*.pt"))))
+
+
+def condition_tensor(g, sd):
+    """The condition image scripts/make_golden.py used: fixed-seed uniform (1,3,ds_h*8,ds_w*8)."""
+    ds = PKG.geometry.low_res_size(g["kwargs"]["height"], g["kwargs"]["width"], sd, 8)
+    return torch.rand(1, 3, ds[0] * 8, ds[1] * 8, generator=torch.Generator().manual_seed(g["cond_seed"]))
 
 
 def load_golden(name):
@@ -50,17 +62,22 @@ def components(sd, device="cpu"):
     return unet, vae, txt, (8 if xl else None)
 
 
-def make_ed(sd, vb, device="cpu"):
+def make_ed(sd, vb, device="cpu", controlnet=False):
     unet, vae, txt, proj = components(sd, device)
+    if controlnet:
+        return PKG.controlnet.ElasticDiffusion.from_components(
+            device, unet, vae, None, txt, sd_version=sd, view_batch_size=vb, projection_dim=proj,
+            controlnet=PKG.synthetic.StubControlNet().to(device))
     return PKG.ElasticDiffusion.from_components(device, unet, vae, None, txt, sd_version=sd, view_batch_size=vb,
                                                 projection_dim=proj)
 
 
-def oracle_models(sd, vb, device="cpu"):
+def oracle_models(sd, vb, device="cpu", controlnet=False):
     from oracle import reference_port as rp
     from oracle.ddim_restated import DDIMRestated
     unet, vae, txt, proj = components(sd, device)
-    return rp.Models(unet, vae, DDIMRestated(), txt, sd, device, vb, projection_dim=proj)
+    cn = PKG.synthetic.StubControlNet().to(device) if controlnet else None
+    return rp.Models(unet, vae, DDIMRestated(), txt, sd, device, vb, projection_dim=proj, controlnet=cn)
 
 
 def oracle_kwargs(kw):

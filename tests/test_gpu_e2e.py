@@ -7,7 +7,8 @@
 import pytest
 import torch
 
-from conftest import PKG, golden_names, load_golden, make_ed, oracle_kwargs, oracle_models
+from conftest import (PKG, cn_golden_names, condition_tensor, golden_names, load_golden, make_ed, oracle_kwargs,
+                      oracle_models)
 from oracle import reference_port as rp
 
 pytestmark = pytest.mark.gpu
@@ -147,3 +148,28 @@ def test_verbose_mode_logs_intermediate_x0_grid():
     ed.seed_everything(0)
     imgs, log = ed.generate_image("a", "b", height=512, width=768, num_inference_steps=2, resampling_steps=1, **NOBAR)
     assert "intermediate_x0_imgs" in log and imgs[0].size == (768, 512)
+
+
+@pytest.mark.parametrize("name", cn_golden_names())
+def test_controlnet_twin_cuda_path_reproduces_reference_goldens(name):
+    g = load_golden(name)
+    ed = make_ed(g["sd_version"], g["view_batch_size"], "cuda", controlnet=True)
+    ed.rng_device = torch.device("cpu")
+    ed.autocast = False
+    ed.seed_everything(g["seed"])
+    lat, _ = ed.denoise(**oracle_kwargs(g["kwargs"]), condition_image=condition_tensor(g, g["sd_version"]),
+                        controlnet_conditioning_scale=g["kwargs"]["controlnet_conditioning_scale"], **NOBAR)
+    mse = torch.mean((lat - g["latent"].cuda()) ** 2).item()
+    assert mse < 1e-8, f"mse {mse:.3e}"
+
+
+def test_controlnet_twin_generate_image_accepts_pil_condition():
+    from PIL import Image
+    import numpy as np
+    ed = make_ed("2.1", 4, "cuda", controlnet=True)
+    ed.autocast = False
+    ed.seed_everything(0)
+    pil = Image.fromarray((np.random.RandomState(0).rand(300, 500, 3) * 255).astype("uint8"))
+    imgs, log = ed.generate_image("a", "b", pil, height=512, width=768, num_inference_steps=2, resampling_steps=1,
+                                  controlnet_conditioning_scale=0.7, **NOBAR)
+    assert imgs[0].size == (768, 512)

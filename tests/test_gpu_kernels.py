@@ -218,3 +218,24 @@ def test_bad_arguments_are_rejected():
     canvas = torch.empty(2, 4, 128, 128, device=DEV)
     assert L.ed_random_pick_gather(ctypes.byref(plan), 1, native.ptr(x), native.ptr(idx), none, native.ptr(canvas), 0,
                                    native.stream_handle()) == -1
+
+
+@pytest.mark.parametrize("cfg", [GEOS[0], GEOS[1], GEOS[5], GEOS[7]])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gather_cond_matches_spec(cfg, dtype):
+    """K12: ControlNet condition batch (zero-padded global condition, nearest-upsampled view crops)."""
+    L = native.lib()
+    geo = build(cfg)
+    plan, keep = upload(geo)
+    window = cfg[5]
+    rm, cm, org = geometry.cond_geometry(geo, 8, window, cfg[3] - window)
+    tabs = [torch.tensor(v, dtype=torch.int32, device=DEV) for v in (rm, cm, org)]
+    R1 = 2
+    cond = torch.rand(2, 3, geo.lh * 8, geo.lw * 8, device=DEV)
+    n = 2 * geo.B * R1 + geo.nv * geo.B
+    out = torch.full((n, 3, geo.native * 8, geo.native * 8), float("nan"), device=DEV, dtype=dtype)
+    native.check(L.ed_gather_cond(ctypes.byref(plan), R1, native.ptr(cond), 3, 8, native.ptr(tabs[0]), native.ptr(tabs[1]),
+                                  native.ptr(tabs[2]), native.ptr(out), native.dtype_code(dtype), native.stream_handle()))
+    torch.cuda.synchronize()
+    want = ws.spec_gather_cond(geo, R1, cond, 8, rm, cm, org).to(dtype)
+    assert torch.equal(out, want)

@@ -7,7 +7,8 @@ import re
 import pytest
 import torch
 
-from conftest import PKG, ROOT, golden_names, load_golden, make_ed, oracle_kwargs, oracle_models
+from conftest import (PKG, ROOT, cn_golden_names, condition_tensor, golden_names, load_golden, make_ed, oracle_kwargs,
+                      oracle_models)
 from oracle import reference_port as rp
 from oracle import wave_spec as ws
 
@@ -173,3 +174,26 @@ def test_wave_form_reproduces_goldens(name):
     # one UNet call per wave instead of one per pass: conv batching may change the last bits on CPU
     assert err <= 2e-5, f"max abs diff {err:.3e}"
     assert torch.mean((lat - g["latent"]) ** 2).item() < 1e-9
+
+
+@pytest.mark.parametrize("name", cn_golden_names())
+def test_wave_form_reproduces_controlnet_goldens(name):
+    """ControlNet twin: condition batch geometry (cond_geometry) + wave batching against the twin's goldens."""
+    g = load_golden(name)
+    ed = make_ed(g["sd_version"], g["view_batch_size"], controlnet=True)
+    ed.seed_everything(g["seed"])
+    lat = ws.denoise_wave_form(ed, **oracle_kwargs(g["kwargs"]), condition_image=condition_tensor(g, g["sd_version"]),
+                               controlnet_conditioning_scale=g["kwargs"]["controlnet_conditioning_scale"])
+    assert (lat - g["latent"]).abs().max().item() <= 2e-5
+
+
+def test_controlnet_twin_signatures_match_reference():
+    import inspect
+    cls = PKG.controlnet.ElasticDiffusion
+    assert list(inspect.signature(cls.__init__).parameters)[1:] == ["device", "sd_version", "controlnet_model", "verbose",
+                                                                     "log_freq", "view_batch_size", "low_vram"]
+    names = list(inspect.signature(cls.generate_image).parameters)[1:]
+    assert names == ["prompts", "negative_prompts", "condition_image", "height", "width", "num_inference_steps",
+                     "guidance_scale", "controlnet_conditioning_scale", "resampling_steps", "new_p", "rrg_stop_t",
+                     "rrg_init_weight", "rrg_scherduler_cls", "cosine_scale", "repaint_sampling", "progress",
+                     "tiled_decoder", "grid"]

@@ -3,7 +3,7 @@ reference (scripts/make_golden.py).  This is what pins the oracle."""
 import pytest
 import torch
 
-from conftest import golden_names, load_golden, oracle_kwargs, oracle_models
+from conftest import cn_golden_names, condition_tensor, golden_names, load_golden, oracle_kwargs, oracle_models
 from oracle import reference_port as rp
 
 FAST = [n for n in golden_names() if "2048x2048" not in n]
@@ -52,3 +52,14 @@ def test_ddim_restated_known_values():
     assert torch.allclose(out["pred_original_sample"], x0, atol=1e-4)
     prev = s.add_noise(x0, eps, t - 100)
     assert torch.allclose(out["prev_sample"], prev, atol=1e-4)
+
+
+@pytest.mark.parametrize("name", cn_golden_names())
+def test_oracle_reproduces_controlnet_twin_latent(name):
+    """goldens from the unmodified elastic_diffusion_w_controlnet.py (scripts/make_golden.py --cn-only)"""
+    g = load_golden(name)
+    m = oracle_models(g["sd_version"], g["view_batch_size"], controlnet=True)
+    rp.seed_all(g["seed"], "cpu")
+    lat = rp.denoise(m, **oracle_kwargs(g["kwargs"]), condition_image=condition_tensor(g, g["sd_version"]),
+                     controlnet_conditioning_scale=g["kwargs"]["controlnet_conditioning_scale"])
+    assert torch.equal(lat, g["latent"]), f"max abs diff {(lat - g['latent']).abs().max().item():.3e}"
