@@ -312,10 +312,13 @@ def run_reference_arm(args):
         return
     res = cpu_reference_sample(args.workload)
     sd, preset, H, W, vb, T, R, cross, pooled = WORKLOADS[args.workload]
+    cfg = workload_config(args.workload, args.gpus)
+    cfg["timing"] = "host wall clock (perf_counter) on the CPU cores; bounded sample, see cpu_baseline.sample"
+    cfg["parallelism"] = f"CPU, {res['cores']} torch threads (rank 0 only)"
     line = {"impl": "reference", "metric": "denoise-steps/sec", "value": res["value"], "unit": "denoise-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / res["value"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.workload, args.gpus), "cpu_baseline": res,
+            "config": cfg, "cpu_baseline": res,
             "e2e": {"value": res["value"], "unit": "denoise-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
