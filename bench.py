@@ -368,6 +368,7 @@ def main():
     ed.autocast = False                 # UNet weights are bf16 already: no per-call weight re-casting
     ed.unet_input_dtype = unet_dtype    # gather kernels write the UNet batch directly in bf16
     ed.use_cuda_graphs = os.environ.get("BENCH_GRAPHS", "1") == "1"   # each wave's UNet forward replayed as a CUDA graph
+    ed.exchange = os.environ.get("BENCH_EXCHANGE", "p2p")              # multi-GPU: fused epilogue + NVLink peer reads
     if os.environ.get("BENCH_CL", "0") == "1":
         unet.to(memory_format=torch.channels_last)
     kw = dict(GEN, height=H, width=Wd, num_inference_steps=T, resampling_steps=R, progress=lambda it: it)
@@ -430,7 +431,8 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args.workload, world),
             "gpu_launches": launches, "clocks": clk,
             "unet": {"calls": ed.last_run["unet_calls"], "samples": ed.last_run["unet_samples"],
-                     "collectives": ed.last_run["collectives"]},
+                     "collectives": ed.last_run["collectives"], "p2p_exchanges": ed.last_run.get("peer_exchanges", 0),
+                     "exchange": ed.exchange, "exchange_fallback": ed.last_run.get("exchange_fallback")},
             "kernels_in_step": {k: {"launches": n, "avg_us": round(1e3 * ms / max(n, 1), 2)} for k, (n, ms) in ktimes.items()}}
     if not args.no_extras:
         sec2, _, d2h = timed_run(host_io=True)

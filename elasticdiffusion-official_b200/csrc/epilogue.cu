@@ -22,6 +22,8 @@ struct EpiArgs {
   const ed_step_params_t* prm;
   const float* latent;
   const void* unet_out;
+  const void* const* peers;   // multi-GPU: device array of `world` base pointers (peer-mapped), sample s lives on rank
+  int world, per;             //   s / per at local index s % per; NULL: all samples in unet_out
   const uint8_t* idx;
   const uint8_t* owner;
   const float* noise;
@@ -130,7 +132,7 @@ __device__ __forceinline__ float local_uncond_walk(const ViewWalk V, const OT* _
 // the channels, the prologue loads of all channels are independent (read-only path, results kept in registers, stores
 // at the end), and the re-noise stream is fetched 4 channels x 4 steps = 16 float4 loads deep before the dependent
 // FMA chain consumes them.  CPT = 1 spreads the channels over gridDim.z (small batches: more CTAs, 8 loads deep).
-template <typename OT, int VEC, int CPT>
+template <typename OT, int VEC, int CPT, bool PEER>
 __global__ void __launch_bounds__(256, ED_EPI_MINB) wave_epilogue_kernel(const EpiArgs A) {
   const ed_plan_t& P = A.P;
   const int xv = blockIdx.x * blockDim.x + threadIdx.x;
@@ -151,6 +153,16 @@ __global__ void __launch_bounds__(256, ED_EPI_MINB) wave_epilogue_kernel(const E
   const long long plane = (long long)P.dH * P.dW;
   const long long sample_stride = (long long)P.C * plane;
   constexpr int KB = 16 / CPT;                                         // re-noise steps fetched per batch
+  // start of UNet-output sample `sidx` (all C channels).  PEER: the sample lives in the symmetric buffer of rank
+  // sidx / per and is read over NVLink with plain P2P loads (no all-gather ran).
+  auto sample = [&](int sidx) -> const OT* {
+    if constexpr (PEER) {
+      const int r = sidx / A.per;
+      return static_cast<const OT*>(A.peers[r]) + (long long)(sidx - r * A.per) * sample_stride;
+    } else {
+      return out + (long long)sidx * sample_stride;
+    }
+  };
 
   PixelRefs ref[VEC];
 #pragma unroll
@@ -165,7 +177,7 @@ __global__ void __launch_bounds__(256, ED_EPI_MINB) wave_epilogue_kernel(const E
     float xin[CPT][VEC], uu[CPT][VEC], dco[CPT][VEC], dun[CPT][VEC];
 #pragma unroll
     for (int cc = 0; cc < CPT; ++cc) {
-      const OT* out_bc = out + ((long long)b * P.C + c_lo + cc) * plane;   // sample 0, batch entry b, channel c
+      const long long ch_off = (long long)(c_lo + cc) * plane;            // channel offset inside a sample
       if constexpr (VEC == 4) {
         const float4 t = __ldg(reinterpret_cast<const float4*>(A.latent + base0 + cc * hw));
         xin[cc][0] = t.x; xin[cc][1] = t.y; xin[cc][2] = t.z; xin[cc][3] = t.w;
@@ -176,9 +188,9 @@ __global__ void __launch_bounds__(256, ED_EPI_MINB) wave_epilogue_kernel(const E
       for (int e = 0; e < VEC; ++e) {
         // pixels covered by several windows (view < 0, overlapping last row / column) are patched after the load phase
         const int v_ = ref[e].view >= 0 ? ref[e].view : 0;
-        uu[cc][e] = ld_ro<OT>(out_bc + (long long)(first_view_sample + v_ * P.B) * sample_stride + ref[e].view_off);
-        dun[cc][e] = ld_ro<OT>(out_bc + (long long)(ref[e].dir_k * 2 + 0) * P.B * sample_stride + ref[e].dir_off);
-        dco[cc][e] = ld_ro<OT>(out_bc + (long long)(ref[e].dir_k * 2 + 1) * P.B * sample_stride + ref[e].dir_off);
+        uu[cc][e] = ld_ro<OT>(sample(first_view_sample + v_ * P.B + b) + ch_off + ref[e].view_off);
+        dun[cc][e] = ld_ro<OT>(sample((ref[e].dir_k * 2 + 0) * P.B + b) + ch_off + ref[e].dir_off);
+        dco[cc][e] = ld_ro<OT>(sample((ref[e].dir_k * 2 + 1) * P.B + b) + ch_off + ref[e].dir_off);
       }
     }
     bool multi = false;
@@ -190,9 +202,24 @@ __global__ void __launch_bounds__(256, ED_EPI_MINB) wave_epilogue_kernel(const E
       for (int cc = 0; cc < CPT; ++cc)
 #pragma unroll
         for (int e = 0; e < VEC; ++e)
-          if (ref[e].view < 0)
-            uu[cc][e] = local_uncond_walk<OT>(V, out + ((long long)b * P.C + c_lo + cc) * plane, sample_stride,
-                                              first_view_sample, y, xv * VEC + e);
+          if (ref[e].view < 0) {
+            // first-writer-wins walk (ed:852-861), sample pointers resolved through sample() (peer-aware)
+            const int x = xv * VEC + e;
+            const int r0 = __ldg(V.vrow_first + y), rn = __ldg(V.vrow_cnt + y);
+            const int c0 = __ldg(V.vcol_first + x), cn = __ldg(V.vcol_cnt + x);
+            float u = 0.f;
+            bool done = false;
+            for (int a = 0; a < rn && !done; ++a)
+              for (int q = 0; q < cn && !done; ++q) {
+                const int v = (r0 + a) * V.nvc + (c0 + q);
+                const int32_t* vt = V.views + v * 8;
+                const int yy = V.v_tp + __ldg(vt + 6) + (y - __ldg(vt + 0));
+                const int xx = V.v_lp + __ldg(vt + 7) + (x - __ldg(vt + 2));
+                u = ld_ro<OT>(sample(first_view_sample + v * V.B + b) + (long long)(c_lo + cc) * plane + (long long)yy * V.dW + xx);
+                done = (u != 0.f);                                       // first writer wins where the value is non-zero
+              }
+            uu[cc][e] = u;
+          }
     }
     // ---- phase B: CFG + DDIM (ed:1031-1035) ------------------------------------------------------------------------------
     float x0v[CPT][VEC];
@@ -225,14 +252,14 @@ __global__ void __launch_bounds__(256, ED_EPI_MINB) wave_epilogue_kernel(const E
 #pragma unroll
       for (int cc = 0; cc < CPT; ++cc) {
         const float* lat_plane = A.latent + ((long long)b * P.C + c_lo + cc) * hw;
-        const OT* out_bc = out + ((long long)b * P.C + c_lo + cc) * plane;
+        const long long ch_off = (long long)(c_lo + cc) * plane;
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
           xl[cc][e] = __ldg(lat_plane + ref[e].lat_off);               // low-res latent of the last iteration (ed:910)
-          ul[cc][e] = ld_ro<OT>(out_bc + (long long)(kl * 2) * P.B * sample_stride + ref[e].dir_off);   // its uncond score
+          ul[cc][e] = ld_ro<OT>(sample(kl * 2 * P.B + b) + ch_off + ref[e].dir_off);   // its uncond score
           // downsampled_direction = nearest-down of the filled full-res direction (ed:688)
-          lun[cc][e] = ld_ro<OT>(out_bc + (long long)(ref[e].ddir_k * 2 + 0) * P.B * sample_stride + ref[e].ddir_off);
-          lco[cc][e] = ld_ro<OT>(out_bc + (long long)(ref[e].ddir_k * 2 + 1) * P.B * sample_stride + ref[e].ddir_off);
+          lun[cc][e] = ld_ro<OT>(sample((ref[e].ddir_k * 2 + 0) * P.B + b) + ch_off + ref[e].ddir_off);
+          lco[cc][e] = ld_ro<OT>(sample((ref[e].ddir_k * 2 + 1) * P.B + b) + ch_off + ref[e].ddir_off);
         }
       }
 #pragma unroll
@@ -361,10 +388,12 @@ int ed_owner_map(const ed_plan_t* plan, int R1, const uint8_t* idx, uint8_t* own
   return ED_OK;
 }
 
-int ed_wave_epilogue(const ed_plan_t* plan, const ed_step_params_t* d_params, const float* latent, const void* unet_out,
-                     int out_dtype, const uint8_t* idx, const uint8_t* owner, const float* noise, float* out_latent,
-                     float* out_x0, void* stream_) {
-  if (!plan || !d_params || !latent || !unet_out || !idx || !owner || !out_latent) return ED_ERR_INVALID;
+static int launch_epilogue(const ed_plan_t* plan, const ed_step_params_t* d_params, const float* latent,
+                           const void* unet_out, const void* const* peers, int world, int per, int out_dtype,
+                           const uint8_t* idx, const uint8_t* owner, const float* noise, float* out_latent, float* out_x0,
+                           void* stream_) {
+  if (!plan || !d_params || !latent || (!unet_out && !peers) || !idx || !owner || !out_latent) return ED_ERR_INVALID;
+  if (peers && (world <= 0 || per <= 0)) return ED_ERR_INVALID;
   const ed_plan_t& P = *plan;
   if (!P.mrow_lo || !P.mrow_n || !P.mcol_lo || !P.mcol_n || !P.up_row || !P.up_col || !P.down_row || !P.down_col ||
       !P.views || !P.vrow_first || !P.vrow_cnt || !P.vcol_first || !P.vcol_cnt || !P.row_src || !P.col_src ||
@@ -372,9 +401,9 @@ int ed_wave_epilogue(const ed_plan_t* plan, const ed_step_params_t* d_params, co
     return ED_ERR_INVALID;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   // channels per thread: 4 when the batch alone fills the GPU, 1 (channels spread over gridDim.z) for small batches
-  const int cpt = (P.C % 4 == 0 && P.B >= 8) ? 4 : 1;
+  const int cpt = (P.C % 4 == 0 && P.B >= 8 && !peers) ? 4 : 1;
   const int c_split = P.C / cpt;
-  EpiArgs A{P, d_params, latent, unet_out, idx, owner, noise, out_latent, out_x0};
+  EpiArgs A{P, d_params, latent, unet_out, peers, world, per, idx, owner, noise, out_latent, out_x0};
   auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const bool vec = (P.W % 4 == 0) && aligned(latent) && aligned(out_latent) && (!out_x0 || aligned(out_x0)) &&
                    (!noise || aligned(noise));
@@ -384,11 +413,14 @@ int ed_wave_epilogue(const ed_plan_t* plan, const ed_step_params_t* d_params, co
   const dim3 block(bx, 256 / bx);
   const dim3 grid((wv + block.x - 1) / block.x, (P.H + block.y - 1) / block.y,
                   P.B * c_split > 65535 ? 65535 : P.B * c_split);
-#define ED_EPI(T)                                                                       \
-  if (vec && cpt == 4) wave_epilogue_kernel<T, 4, 4><<<grid, block, 0, stream>>>(A);     \
-  else if (vec) wave_epilogue_kernel<T, 4, 1><<<grid, block, 0, stream>>>(A);            \
-  else if (cpt == 4) wave_epilogue_kernel<T, 1, 4><<<grid, block, 0, stream>>>(A);       \
-  else wave_epilogue_kernel<T, 1, 1><<<grid, block, 0, stream>>>(A);
+#define ED_EPI(T)                                                                                   \
+  if (peers) {                                                                                      \
+    if (vec) wave_epilogue_kernel<T, 4, 1, true><<<grid, block, 0, stream>>>(A);                     \
+    else wave_epilogue_kernel<T, 1, 1, true><<<grid, block, 0, stream>>>(A);                         \
+  } else if (vec && cpt == 4) wave_epilogue_kernel<T, 4, 4, false><<<grid, block, 0, stream>>>(A);   \
+  else if (vec) wave_epilogue_kernel<T, 4, 1, false><<<grid, block, 0, stream>>>(A);                 \
+  else if (cpt == 4) wave_epilogue_kernel<T, 1, 4, false><<<grid, block, 0, stream>>>(A);            \
+  else wave_epilogue_kernel<T, 1, 1, false><<<grid, block, 0, stream>>>(A);
   switch (out_dtype) {
     case ED_F32: ED_EPI(float) break;
     case ED_F16: ED_EPI(__half) break;
@@ -398,6 +430,20 @@ int ed_wave_epilogue(const ed_plan_t* plan, const ed_step_params_t* d_params, co
 #undef ED_EPI
   ED_LAUNCH_CHECK();
   return ED_OK;
+}
+
+int ed_wave_epilogue(const ed_plan_t* plan, const ed_step_params_t* d_params, const float* latent, const void* unet_out,
+                     int out_dtype, const uint8_t* idx, const uint8_t* owner, const float* noise, float* out_latent,
+                     float* out_x0, void* stream_) {
+  return launch_epilogue(plan, d_params, latent, unet_out, nullptr, 0, 0, out_dtype, idx, owner, noise, out_latent, out_x0,
+                         stream_);
+}
+
+int ed_wave_epilogue_peer(const ed_plan_t* plan, const ed_step_params_t* d_params, const float* latent,
+                          const void* const* d_peer_out, int world, int per, int out_dtype, const uint8_t* idx,
+                          const uint8_t* owner, const float* noise, float* out_latent, float* out_x0, void* stream_) {
+  return launch_epilogue(plan, d_params, latent, nullptr, d_peer_out, world, per, out_dtype, idx, owner, noise, out_latent,
+                         out_x0, stream_);
 }
 
 int ed_renoise(const ed_step_params_t* d_params, const float* x, const float* noise, float* out, int64_t numel,

@@ -267,6 +267,13 @@ class RngLedger:
 
 
 # ---------------------------------------------------------------------------------------------------------------
+class PeerOut:
+    """UNet outputs of a sharded wave left in the ranks' symmetric buffers (read by ed_wave_epilogue_peer)."""
+
+    def __init__(self, ptrs, world, per, dtype):
+        self.ptrs, self.world, self.per, self.dtype = ptrs, world, per, dtype
+
+
 class ElasticDiffusion(nn.Module):
     def __init__(self, device, sd_version='2.0',
                  verbose=False,
@@ -318,6 +325,9 @@ class ElasticDiffusion(nn.Module):
         self.unet_batch_limit = None  # max samples per UNet call (None: the whole wave in one call)
         self.dist_group = None        # torch.distributed group to shard wave samples over (None: WORLD if initialised)
         self.shard_waves = True
+        self.exchange = "p2p"         # multi-GPU exchange of UNet outputs: "p2p" = symmetric-memory buffers read by the fused
+                                      # epilogue over NVLink (no collective), "nccl" = all_gather_into_tensor per wave
+        self._sym = None
         self.unet_input_dtype = None  # dtype the gather kernels write the UNet batch in (None: fp32 like the reference)
         self.use_cuda_graphs = False  # capture each wave's UNet forward in a CUDA graph (static canvas / text buffers)
         self._graphs = {}
@@ -556,12 +566,45 @@ class ElasticDiffusion(nn.Module):
             probe = torch.tensor([native.dtype_code(mine.dtype) if mine.numel() else -1], device=self.device)
             dist.all_reduce(probe, op=dist.ReduceOp.MAX, group=grp)
             self._shard_dtype = {0: torch.float32, 1: torch.float16, 2: torch.bfloat16}[int(probe.item())]
+        if self.exchange == "p2p" and self._sym is None:
+            self._sym = self._setup_symmetric(per, tuple(canvas.shape[1:]), self._shard_dtype, grp, ws)
+        if self.exchange == "p2p" and self._sym:
+            # leave the local outputs in this rank's symmetric buffer; the epilogue kernel of every rank reads the samples
+            # it needs straight from their owners over NVLink after a device-side barrier (no all-gather)
+            sym = self._sym
+            slot = sym["slot"] = sym["slot"] ^ 1
+            if per > sym["per_max"]:
+                raise RuntimeError("symmetric exchange buffer too small for this wave")
+            sym["bufs"][slot][:hi - lo].copy_(mine)
+            sym["hdls"][slot].barrier(channel=0)
+            self.last_run["peer_exchanges"] = self.last_run.get("peer_exchanges", 0) + 1
+            return PeerOut(sym["ptrs"][slot], ws, per, self._shard_dtype)
         send = torch.zeros((per,) + tuple(canvas.shape[1:]), device=self.device, dtype=self._shard_dtype)
         send[:hi - lo] = mine
         gathered = torch.empty((ws * per,) + tuple(canvas.shape[1:]), device=self.device, dtype=self._shard_dtype)
         dist.all_gather_into_tensor(gathered, send, group=grp)
         self.last_run["collectives"] += 1
         return gathered[:n]
+
+    def _setup_symmetric(self, per_max, tail, dtype, grp, ws):
+        """Two symmetric-memory buffers (alternating per wave) for the rank-local UNet outputs + peer pointer tables.
+        Falls back to the NCCL all-gather (with a note in last_run) when symmetric memory is unavailable."""
+        try:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm
+            group = grp if grp is not None else dist.group.WORLD
+            bufs, hdls, ptrs = [], [], []
+            for _ in range(2):
+                t = symm.empty((per_max,) + tail, dtype=dtype, device=self.device)
+                h = symm.rendezvous(t, group)
+                bufs.append(t)
+                hdls.append(h)
+                ptrs.append(torch.tensor([int(p) for p in h.buffer_ptrs], dtype=torch.int64, device=self.device))
+            return dict(bufs=bufs, hdls=hdls, ptrs=ptrs, slot=0, per_max=per_max)
+        except Exception as e:  # pragma: no cover - depends on the box
+            self.last_run["exchange_fallback"] = f"symmetric memory unavailable ({type(e).__name__}: {e}); using nccl all_gather"
+            self.exchange = "nccl"
+            return {}
 
     @torch.no_grad()
     def generate_image(self, prompts, negative_prompts='',
@@ -613,6 +656,7 @@ class ElasticDiffusion(nn.Module):
             raise TypeError(f"height {height} and Width {width} must be divisable by {sf}")   # ed:200-201 raises a str
         self.last_run = dict(kernel_launches=0, unet_calls=0, unet_samples=0, collectives=0, vae_encodes=0, steps=0)
         self._shard_dtype = None
+        self._sym = None
         self._x0_log = []
         ds = self.get_downsample_size(height, width)                                           # ed:968
         self.default_size = (4 * height, 4 * width)                                            # ed:969
@@ -745,10 +789,16 @@ class ElasticDiffusion(nn.Module):
             if out.dtype == torch.float16:
                 prm.flags |= native.FLAG_FP16_SEM
             native.check(L.ed_upload_step_params(native.ptr(d_params[slot]), ctypes.byref(prm), st), "upload")
-            launch("ed_wave_epilogue" + ("+renoise" if prm.flags & 1 else "+rrg" if prm.flags & 2 else ""),
-                   L.ed_wave_epilogue, ctypes.byref(plan), native.ptr(d_params[slot]), native.ptr(x_in),
-                   native.ptr(out), native.dtype_code(out.dtype), native.ptr(idx_dev), native.ptr(owner),
-                   native.ptr(noise_buf), native.ptr(x_out), native.ptr(x0_out), st)
+            tag = "+renoise" if prm.flags & 1 else "+rrg" if prm.flags & 2 else ""
+            if isinstance(out, PeerOut):
+                launch("ed_wave_epilogue_peer" + tag, L.ed_wave_epilogue_peer, ctypes.byref(plan),
+                       native.ptr(d_params[slot]), native.ptr(x_in), native.ptr(out.ptrs), out.world, out.per,
+                       native.dtype_code(out.dtype), native.ptr(idx_dev), native.ptr(owner), native.ptr(noise_buf),
+                       native.ptr(x_out), native.ptr(x0_out), st)
+            else:
+                launch("ed_wave_epilogue" + tag, L.ed_wave_epilogue, ctypes.byref(plan), native.ptr(d_params[slot]),
+                       native.ptr(x_in), native.ptr(out), native.dtype_code(out.dtype), native.ptr(idx_dev),
+                       native.ptr(owner), native.ptr(noise_buf), native.ptr(x_out), native.ptr(x0_out), st)
             return out
 
         def plan_step(i):

@@ -153,6 +153,16 @@ int ed_wave_epilogue(const ed_plan_t* plan, const ed_step_params_t* d_params, co
                      const void* unet_out, int out_dtype, const uint8_t* idx, const uint8_t* owner,
                      const float* noise, float* out_latent, float* out_x0, void* stream);
 
+/* ---- C1: the same epilogue fused with the multi-GPU exchange ---------------------------------
+ * With wave samples sharded over `world` ranks (rank r holds samples [r*per, (r+1)*per) of the wave layout in its own
+ * buffer), no all-gather is run: `d_peer_out` is a DEVICE array of `world` pointers to the ranks' buffers, all mapped
+ * into this process (symmetric memory / CUDA IPC), and the kernel reads every sample it needs straight from its owner
+ * over NVLink (P2P ld.global).  The caller orders "all ranks finished their UNet" before the launch (device-side
+ * symmetric-memory barrier).  Every rank runs the (replicated, microsecond) epilogue itself. */
+int ed_wave_epilogue_peer(const ed_plan_t* plan, const ed_step_params_t* d_params, const float* latent,
+                          const void* const* d_peer_out, int world, int per, int out_dtype, const uint8_t* idx,
+                          const uint8_t* owner, const float* noise, float* out_latent, float* out_x0, void* stream);
+
 /* ---- K7 alone: x <- a_k*x + b_k*eps_k, k = 0..n-1 in sequence (ed:692-704) ---------------------------------- */
 int ed_renoise(const ed_step_params_t* d_params, const float* x, const float* noise, float* out,
                int64_t numel, void* stream);

@@ -16,11 +16,13 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 rank, world = dist.get_rank(), dist.get_world_size()
 ok = True
-for name in ("xl_1024x2048_T3_R7", "sd21_512x1024_B2_T3_R2", "xl_2048x2048_T2_R2_tiled"):
+for name, mode in [("xl_1024x2048_T3_R7", "p2p"), ("xl_1024x2048_T3_R7", "nccl"), ("sd21_512x1024_B2_T3_R2", "p2p"),
+                   ("xl_2048x2048_T2_R2_tiled", "p2p"), ("xl_1080x1920_T2_R2", "p2p")]:
     g = load_golden(name)
     ed = make_ed(g["sd_version"], g["view_batch_size"], f"cuda:{local}")
     ed.rng_device = torch.device("cpu")
     ed.autocast = False
+    ed.exchange = mode
     ed.seed_everything(g["seed"])
     lat, _ = ed.denoise(**oracle_kwargs(g["kwargs"]), progress=lambda it: it)
     mse = torch.mean((lat.cpu() - g["latent"]) ** 2).item()
@@ -28,10 +30,12 @@ for name in ("xl_1024x2048_T3_R7", "sd21_512x1024_B2_T3_R2", "xl_2048x2048_T2_R2
     ref0 = lat.clone()
     dist.broadcast(ref0, src=0)
     same = torch.equal(ref0, lat)
-    ok &= mse < 1e-8 and same and ed.last_run["collectives"] > 0
+    exchanged = ed.last_run["collectives"] + ed.last_run.get("peer_exchanges", 0)
+    ok &= mse < 1e-8 and same and exchanged > 0
     if rank == 0:
-        print(f"{name}: world={world} mse_vs_reference_golden={mse:.3e} identical_on_all_ranks={same} "
-              f"collectives={ed.last_run['collectives']} unet_samples_rank0={ed.last_run['unet_samples']}")
+        print(f"{name} [{mode}]: world={world} mse_vs_reference_golden={mse:.3e} identical_on_all_ranks={same} "
+              f"nccl_collectives={ed.last_run['collectives']} p2p_exchanges={ed.last_run.get('peer_exchanges', 0)} "
+              f"fallback={ed.last_run.get('exchange_fallback')} unet_samples_rank0={ed.last_run['unet_samples']}")
 flag = torch.tensor([int(ok)], device=f"cuda:{local}")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
