@@ -446,7 +446,11 @@ def main():
             roof, peak, how = kernel_rooflines(device)
             dom = "ed_wave_epilogue+renoise"
             line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": roof[dom]["GB/s"], "peak": peak,
-                                "unit": "GB/s", "frac": roof[dom]["frac"], "traffic": None, "peak_source": how,
+                                "unit": "GB/s", "frac": roof[dom]["frac"],
+                                # DRAM read+write bytes of one launch at exactly these sizes, from the committed
+                                # `ncu --set full` capture profiles/r1_epi_renoise3.ncu-rep (1.10 x algorithmic bytes)
+                                "traffic": 1.2598e9, "algorithmic_bytes": roof[dom]["algorithmic_MB"] * 1e6,
+                                "peak_source": how,
                                 "sizes": "B=96 SDXL 1024x2048 latents per launch (L2-exceeding); in-pipeline launches are "
                                          "L2-resident and latency-bound, see kernels_in_step"}
             line["roofline_all"] = roof
@@ -462,8 +466,9 @@ def main():
                 line["reference_gpu_eager"] = {"error": repr(e)[:200]}
             line["cpu_baseline"] = cpu_reference_sample(args.workload)
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
