@@ -127,10 +127,13 @@ class RngLedger:
         self.rng_dev = owner.rng_device if owner.rng_device is not None else owner.device
         self.strip_cache = {}
         self.n_cells = geo.lh * geo.lw
+        self._rows = np.arange(self.n_cells)
         # device draws whose VALUES the host needs (drop masks, ed:541) run on a side stream so that reading them back
         # never waits for the UNet work queued on the main stream (Philox offsets are assigned at call time on the
         # host, so the stream a draw runs on does not change its values)
-        self._side = torch.cuda.Stream(device=self.dev) if self.rng_dev.type == "cuda" else None
+        # HIGH priority: measured on B200 (scripts/side_stream_probe.py), a launch on a default-priority stream blocks the
+        # host until the CUDA graph running on the main stream has finished; a high-priority stream issues in ~0.2 ms
+        self._side = torch.cuda.Stream(device=self.dev, priority=-1) if self.rng_dev.type == "cuda" else None
         self._side_ev = torch.cuda.Event() if self._side is not None else None
         self._drop_pinned = torch.empty(self.n_cells, dtype=torch.int64).pin_memory() if self._side is not None else None
 
@@ -148,9 +151,13 @@ class RngLedger:
 
     # -- seeds (ed:165-171, 321-324) -----------------------------------------------------------------------------
     def _seed(self, seed):
-        torch.manual_seed(seed)
+        """seed_everything(seed, seed_np=False) of ed:165-168 for the generators this process draws from: the CPU default
+        generator and this device's CUDA generator.  (torch.manual_seed also walks every other visible device and
+        backend hook, ~0.7 ms per call x 36 calls per step; seeding the two generators directly is equivalent here.)"""
+        torch.default_generator.manual_seed(seed)
         if self.dev.type == "cuda":
-            torch.cuda.manual_seed(seed)
+            idx = self.dev.index if self.dev.index is not None else torch.cuda.current_device()
+            torch.cuda.default_generators[idx].manual_seed(seed)
 
     @staticmethod
     def _md5_seed(s):
@@ -188,7 +195,11 @@ class RngLedger:
                                                            dtype=dist.mean.dtype).to(self.dev)
                 z = z * o.vae.config.scaling_factor
                 noise = self._randn(z.shape, z.dtype)
-                hit = o.scheduler.add_noise(z, noise, t.long()).float().contiguous()
+                # scheduler.add_noise (ed:358) = sqrt(abar_t) z + sqrt(1-abar_t) noise.  Its .to(device) of the schedule
+                # table is a synchronous pageable H2D copy, i.e. a full GPU sync per strip that would serialise the
+                # look-ahead planning with the UNet; the two fp32 scalars are taken on the host instead (same values).
+                ac = o.scheduler.alphas_cumprod[int(t)]
+                hit = (float(ac ** 0.5) * z + float((1 - ac) ** 0.5) * noise).float().contiguous()
                 if upcast:
                     o.vae.to(dtype=torch.float16)
             self.strip_cache[key] = hit
@@ -213,19 +224,32 @@ class RngLedger:
 
     # -- per-cell pick indices (ed:502-520, 534-544, 673-675) -------------------------------------------------------
     def _draw_cells(self, exclude):
+        """ed:502-520 with identical generator consumption: `exclude` is an (n,4) bool numpy array.  The draws are the
+        same torch.randint calls (sizes n, then the number of still-invalid cells per round, <= 50 rounds, then the
+        final unconditional redraw); the bookkeeping runs in numpy, and once only cells with all four picks excluded
+        remain invalid the remaining rounds are just their (parity-relevant) draws without index work."""
         n = self.n_cells
-        idx = torch.randint(0, 4, (n,))
-        rows = torch.arange(n)
-        rounds = 50
+        rows = self._rows
+        idx = torch.randint(0, 4, (n,)).numpy()
         bad = exclude[rows, idx]
         m = int(bad.sum())
+        rounds = 50
+        hopeless = None
         while m > 0 and rounds > 0:
-            idx[bad] = torch.randint(0, 4, (m,))
+            if hopeless is None:
+                hopeless = exclude.all(axis=1)
+            if hopeless[bad].all():
+                for _ in range(rounds):
+                    last = torch.randint(0, 4, (m,))
+                idx[bad] = last.numpy()
+                rounds = 0
+                break
+            idx[bad] = torch.randint(0, 4, (m,)).numpy()
             bad = exclude[rows, idx]
             m = int(bad.sum())
             rounds -= 1
         if m > 0:
-            idx[bad] = torch.randint(0, 4, (m,))
+            idx[bad] = torch.randint(0, 4, (m,)).numpy()
         return idx
 
     def global_pass(self, t, resampling_steps, drop_p):
@@ -233,22 +257,23 @@ class RngLedger:
         Returns (idx uint8 host tensor (R+1, n_cells), strips)."""
         g = self.geo
         n = self.n_cells
-        out = torch.zeros(resampling_steps + 1, n, dtype=torch.uint8)
-        exclude = torch.zeros(n, 4, dtype=torch.bool)
-        rows = torch.arange(n)
-        prev = torch.zeros(n, dtype=torch.long)                                    # k = 0: top-left pick (ed:536)
+        out = np.zeros((resampling_steps + 1, n), dtype=np.uint8)
+        exclude = np.zeros((n, 4), dtype=bool)
+        rows = self._rows
+        prev = np.zeros(n, dtype=np.int64)                                         # k = 0: top-left pick (ed:536)
         strips = None
+        thr = 100 * drop_p
         for k in range(resampling_steps + 1):
             if k > 0:
                 idx = self._draw_cells(exclude)
-                drop = self._drop_draw()                                           # ed:541
-                drop[drop <= (100 * drop_p)] = 0
-                drop[drop >= (100 * drop_p)] = 1
-                prev = idx * drop + prev * (1 - drop)
+                drop = self._drop_draw().numpy().copy()                            # ed:541
+                drop[drop <= thr] = 0                                              # ed:542
+                drop[drop >= thr] = 1                                              # ed:543 -> P(new) = 30/101 at new_p = 0.3
+                prev = idx * drop + prev * (1 - drop)                              # ed:544
             exclude[rows, prev] = True                                             # ed:675
-            out[k] = prev.to(torch.uint8)
+            out[k] = prev.astype(np.uint8)
             strips = self.pad_events(g.lh, g.lw, t)                                # unet_step of this iteration
-        return out, strips
+        return torch.from_numpy(out), strips
 
     def local_pass(self, t, view_batch_size):
         """RNG side effects of `compute_local_uncond_signal` (ed:830-850): one padded unet_step per view chunk."""
