@@ -31,6 +31,9 @@ CASES = {
                                                    tiled_decoder=True)),
     "xl_1536x1536_T2_R3": ("XL1.0", 16, dict(height=1536, width=1536, num_inference_steps=2, resampling_steps=3)),
     "xl_1080x1920_T2_R2": ("XL1.0", 4, dict(height=1080, width=1920, num_inference_steps=2, resampling_steps=2)),
+    # latent 96x256: window+context >= 96 -> the window collapses to the full height (ed:820-825) and every view is
+    # 96 rows < native 128 -> background-padded local views (ed:405-408 from compute_local_uncond_signal), 2 view chunks
+    "xl_768x2048_T2_R2_padded_views": ("XL1.0", 2, dict(height=768, width=2048, num_inference_steps=2, resampling_steps=2)),
 }
 # ControlNet twin (elastic_diffusion_w_controlnet.py): condition = fixed-seed uniform image of the prepared size
 CN_CASES = {
@@ -100,6 +103,10 @@ def main_cn():
 
 
 if __name__ == "__main__":
+    only = [a for a in sys.argv[1:] if a in CASES]
+    if only:
+        CASES = {k: CASES[k] for k in only}
+        main_cn = lambda: None
     if "--cn-only" in sys.argv:
         main_cn()
         sys.exit(0)

@@ -48,7 +48,8 @@ GEOS = [(1, 128, 256, 128, (64, 128), 64),      # cfg3  SDXL 1024x2048
         (1, 135, 240, 128, (72, 128), 64),      # 1080x1920: odd width -> non-TMA / non-vector paths, overlapping views
         (1, 80, 112, 64, (45, 64), 32),         # ragged SD
         (1, 96, 128, 64, (48, 64), 32),
-        (1, 128, 256, 128, (64, 128), 32)]      # patch_size=32: overlapping last windows
+        (1, 128, 256, 128, (64, 128), 32),      # patch_size=32: overlapping last windows
+        (2, 96, 256, 128, (48, 128), 64)]       # window collapse: views 96 rows < native 128 -> ed_pad_views, v_tp offsets
 
 
 def build(cfg):

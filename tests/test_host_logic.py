@@ -68,7 +68,8 @@ def test_signatures_match_reference():
 # ---- geometry vs oracle ---------------------------------------------------------------------------------------------
 SHAPES = [(64, 128, (32, 64), 64, 32), (128, 256, (64, 128), 128, 64), (192, 192, (128, 128), 128, 64),
           (135, 240, (72, 128), 128, 64), (64, 64, (64, 64), 64, 32), (80, 112, (45, 64), 64, 32),
-          (256, 256, (128, 128), 128, 64), (96, 128, (48, 64), 64, 32), (128, 256, (64, 128), 128, 32)]
+          (256, 256, (128, 128), 128, 64), (96, 128, (48, 64), 64, 32), (128, 256, (64, 128), 128, 32),
+          (96, 256, (48, 128), 128, 64)]
 
 
 @pytest.mark.parametrize("H,W,ds,native_sz,window", SHAPES)
