@@ -34,6 +34,10 @@ CASES = {
     # latent 96x256: window+context >= 96 -> the window collapses to the full height (ed:820-825) and every view is
     # 96 rows < native 128 -> background-padded local views (ed:405-408 from compute_local_uncond_signal), 2 view chunks
     "xl_768x2048_T2_R2_padded_views": ("XL1.0", 2, dict(height=768, width=2048, num_inference_steps=2, resampling_steps=2)),
+    # downsample factors > 2 (the reference's "Future TODO" ed:562 - it does run, keeping 2 of every
+    # 8 / 6 rows of the 2x-resized grid): factor 4 (latent 128x256 -> low-res 32x64) and factor 3 (192x192 -> 64x64)
+    "sd21_1024x2048_T2_R3_factor4": ("2.1", 8, dict(height=1024, width=2048, num_inference_steps=2, resampling_steps=3)),
+    "sd21_1536x1536_T2_R2_factor3": ("2.1", 4, dict(height=1536, width=1536, num_inference_steps=2, resampling_steps=2)),
 }
 # ControlNet twin (elastic_diffusion_w_controlnet.py): condition = fixed-seed uniform image of the prepared size
 CN_CASES = {
