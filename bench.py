@@ -103,6 +103,16 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` at the roofline sizes, recorded in
+    profiles/traffic.json from an `ncu --set full` capture (null when no capture of the current kernel exists)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    ent = json.load(open(p)).get(kernel)
+    return float(ent["bytes"]) if ent else None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -114,9 +124,31 @@ def peaks():
 # ---------------------------------------------------------------------------------------------------------------
 # L2-exceeding kernel roofline (live, CUDA events on the launching stream)
 # ---------------------------------------------------------------------------------------------------------------
-def kernel_rooflines(device, B=96, out_dtype=torch.bfloat16, iters=10, warm=3):
+def needed_global_elements(geo, R1, idx, owner, rrg):
+    """Distinct (iteration, cond/uncond, low-res cell) elements of the global-pass UNet outputs that the epilogue's
+    arithmetic needs for ONE (batch entry, channel): per full-res pixel the cond and uncond scores of the iteration that
+    owns it at the cell nearest-upsampling reads (ed:634-647); with RRG also the last iteration's uncond score at every
+    cell and cond/uncond of the owner at the pixel nearest-downsampling reads (ed:686-688, 909-918).  Counted exactly from
+    the owner map (the algorithmic minimum; a sector-granular memory system moves more, see `traffic`)."""
+    dev = owner.device
+    t = lambda k: torch.tensor(geo.tables[k], dtype=torch.long, device=dev)
+    pix = t("pix_ref").view(-1, 4)
+    cells = geo.lh * geo.lw
+    own = owner.long()
+    keys = [(own * 2 + s) * cells + pix[:, 3] for s in (0, 1)]
+    if rrg:
+        down = t("cell_down").view(-1, 2)
+        kd = own[down[:, 0]]
+        dcell = pix[down[:, 0], 3]
+        keys += [((R1 - 1) * 2) * cells + torch.arange(cells, device=dev), (kd * 2) * cells + dcell, (kd * 2 + 1) * cells + dcell]
+    return int(torch.unique(torch.cat(keys)).numel())
+
+
+def kernel_rooflines(device, B=96, out_dtype=torch.bfloat16, iters=10, warm=3, only=None, ab=True):
     """Times every hot-path kernel of libelastic_b200 on a batch of B SDXL 1024x2048 latents (working sets of
-    0.1-1.3 GiB, all larger than the 126 MB L2) and returns algorithmic GB/s per kernel."""
+    0.1-1.3 GiB, all larger than the 126 MB L2) and returns algorithmic GB/s per kernel.  Algorithmic bytes = every
+    distinct input element the op needs, read once, + every output element, written once.  `ab`: also time the
+    direct (scattered-load) epilogue kernel next to the default tile-staged one."""
     P = pkg()
     native, geometry = P.native, P.geometry
     L = native.lib()
@@ -130,28 +162,47 @@ def kernel_rooflines(device, B=96, out_dtype=torch.bfloat16, iters=10, warm=3):
     st = native.stream_handle()
     x = torch.randn(B, C, H, W, device=device)
     y = torch.empty_like(x)
-    idx = torch.randint(0, 4, (R1, geo.lh * geo.lw), device=device, dtype=torch.uint8)
+    cells = geo.lh * geo.lw
+    idx = torch.randint(0, 4, (R1, cells), device=device, dtype=torch.uint8)
     idx[0] = 0
+    idx_w2 = torch.zeros(1, cells, device=device, dtype=torch.uint8)          # wave 2 of a repaint step: one iteration
     strips = [None, None, torch.randn(1, C, tp, nat, device=device), torch.randn(1, C, bp, nat, device=device)]
     n = 2 * B * R1 + geo.nv * B
     so = torch.empty(0, dtype=out_dtype).element_size()
     canvas32 = torch.empty(geo.nv * B, C, nat, nat, device=device)
     canvas = torch.empty(n, C, nat, nat, device=device, dtype=out_dtype)
     out = torch.randn(n, C, nat, nat, device=device, dtype=torch.float32).to(out_dtype)
+    out_w2 = out[:2 * B + geo.nv * B]
     noise = torch.randn(n_re, B, C, H, W, device=device)
-    sp = native.StepParams(guidance=10.0, sqrt_beta_t=0.96, sqrt_alpha_t=0.27, sqrt_alpha_prev=0.33, sqrt_dir=0.94,
-                           rrg_weight=700.0, rrg_norm=2.0 / (C * H * W), flags=1, n_renoise=n_re, R1=R1)
-    for k in range(n_re):
-        sp.renoise_a[k], sp.renoise_b[k] = 0.995, 0.1
-    d_prm = torch.empty(2, ctypes.sizeof(native.StepParams), dtype=torch.uint8, device=device)
-    native.check(L.ed_upload_step_params(native.ptr(d_prm[0]), ctypes.byref(sp), st))
-    sp.flags = 2
-    native.check(L.ed_upload_step_params(native.ptr(d_prm[1]), ctypes.byref(sp), st))
+    d_prm = torch.empty(3, ctypes.sizeof(native.StepParams), dtype=torch.uint8, device=device)
+    for slot, (flags, r1) in enumerate([(1, R1), (2, R1), (2, 1)]):
+        sp = native.StepParams(guidance=10.0, sqrt_beta_t=0.96, sqrt_alpha_t=0.27, sqrt_alpha_prev=0.33, sqrt_dir=0.94,
+                               rrg_weight=700.0, rrg_norm=2.0 / (C * H * W), flags=flags, n_renoise=n_re, R1=r1)
+        for k in range(n_re):
+            sp.renoise_a[k], sp.renoise_b[k] = 0.995, 0.1
+        native.check(L.ed_upload_step_params(native.ptr(d_prm[slot]), ctypes.byref(sp), st))
     owner = torch.empty(H * W, dtype=torch.uint8, device=device)
     native.check(L.ed_owner_map(ctypes.byref(plan), R1, native.ptr(idx), native.ptr(owner), st))
+    owner_w2 = torch.zeros(H * W, dtype=torch.uint8, device=device)
     Lb = B * C * H * W * 4
-    low = B * C * geo.lh * geo.lw
+    low = B * C * cells
     win = geo.nv * B * C * 128 * 64          # windows tile the latent exactly at this shape
+    glob = lambda r1, ix, ow, rrg: needed_global_elements(geo, r1, ix, ow, rrg) * B * C * so
+
+    def epi(slot, r1, o, ix, ow, nz):
+        return lambda: L.ed_wave_epilogue(ctypes.byref(plan), native.ptr(d_prm[slot]), r1, native.ptr(x), native.ptr(o),
+                                          native.dtype_code(out_dtype), native.ptr(ix), native.ptr(ow), nz, native.ptr(y), None, st)
+    epi_cases = {
+        # wave 1 of a repaint step (cfg3: R1 = 8): latent + windows + needed global elements + owner bytes + 20 noise + out
+        "ed_wave_epilogue+renoise": (epi(0, R1, out, idx, owner, native.ptr(noise)),
+                                     Lb + win * so + glob(R1, idx, owner, False) + H * W + n_re * Lb + Lb),
+        # wave 2 of a repaint step while RRG is active (cfg3: one iteration) - the RRG launch of the BASELINE config
+        "ed_wave_epilogue+rrg(wave2,R1=1)": (epi(2, 1, out_w2, idx_w2, owner_w2, None),
+                                             Lb + win * so + glob(1, idx_w2, owner_w2, True) + H * W + cells + Lb),
+        # repaint_sampling=False: RRG in the R1 = 8 wave
+        "ed_wave_epilogue+rrg": (epi(1, R1, out, idx, owner, None),
+                                 Lb + win * so + glob(R1, idx, owner, True) + H * W + cells + Lb),
+    }
     cases = {
         "ed_gather_views(tma)": (
             lambda: L.ed_gather_views(ctypes.byref(plan), native.ptr(x), native.ptr(canvas32), native.ED_F32, 0, st),
@@ -159,20 +210,12 @@ def kernel_rooflines(device, B=96, out_dtype=torch.bfloat16, iters=10, warm=3):
         "ed_random_pick_gather": (
             lambda: L.ed_random_pick_gather(ctypes.byref(plan), R1, native.ptr(x), native.ptr(idx),
                                             native.strips_array(strips), native.ptr(canvas), native.dtype_code(out_dtype), st),
-            R1 * (low * 4 + geo.lh * geo.lw + 2 * B * C * nat * nat * so)),
-        "ed_wave_epilogue+renoise": (
-            lambda: L.ed_wave_epilogue(ctypes.byref(plan), native.ptr(d_prm[0]), native.ptr(x), native.ptr(out),
-                                       native.dtype_code(out_dtype), native.ptr(idx), native.ptr(owner), native.ptr(noise),
-                                       native.ptr(y), None, st),
-            Lb + win * so + 2 * low * so + R1 * geo.lh * geo.lw + n_re * Lb + Lb),
-        "ed_wave_epilogue+rrg": (
-            lambda: L.ed_wave_epilogue(ctypes.byref(plan), native.ptr(d_prm[1]), native.ptr(x), native.ptr(out),
-                                       native.dtype_code(out_dtype), native.ptr(idx), native.ptr(owner), None, native.ptr(y), None, st),
-            Lb + win * so + 2 * low * so + R1 * geo.lh * geo.lw + low * 4 + low * so + Lb),
-        "ed_renoise": (
-            lambda: L.ed_renoise(native.ptr(d_prm[0]), native.ptr(x), native.ptr(noise), native.ptr(y), x.numel(), st),
-            (2 + n_re) * Lb),
+            R1 * (low * 4 + cells + 2 * B * C * nat * nat * so)),
     }
+    cases.update(epi_cases)
+    cases["ed_renoise"] = (
+        lambda: L.ed_renoise(native.ptr(d_prm[0]), native.ptr(x), native.ptr(noise), native.ptr(y), x.numel(), st),
+        (2 + n_re) * Lb)
     # tiled-decode blend at cfg4's shape: 64 tiles x (3,1024,1024) decoded patches -> (3,2048,2048), batch 4
     tg = geometry.build_tiles(256, 256, 128, 8)
     tb = 4
@@ -195,7 +238,8 @@ def kernel_rooflines(device, B=96, out_dtype=torch.bfloat16, iters=10, warm=3):
         zl.numel() * 4 + boxes.numel() * 4)      # every latent element read at least once + all boxes written
     peak, how = peaks()
     res = {}
-    for name, (fn, nbytes) in cases.items():
+
+    def time_case(name, fn, nbytes):
         for _ in range(warm):
             native.check(fn(), name)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -207,8 +251,19 @@ def kernel_rooflines(device, B=96, out_dtype=torch.bfloat16, iters=10, warm=3):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
         gbs = nbytes / ms / 1e6
-        res[name] = {"ms": round(ms, 4), "algorithmic_MB": round(nbytes / 1e6, 1), "GB/s": round(gbs, 1),
-                     "frac": round(gbs / peak, 3)}
+        return {"ms": round(ms, 4), "algorithmic_MB": round(nbytes / 1e6, 1), "GB/s": round(gbs, 1), "frac": round(gbs / peak, 3)}
+
+    for name, (fn, nbytes) in cases.items():
+        if only and name not in only:
+            continue
+        res[name] = time_case(name, fn, nbytes)
+    if ab and not only:     # A/B: the direct (scattered-load) epilogue kernel on the same inputs
+        native.check(L.ed_set_epilogue_mode(native.EPILOGUE_DIRECT))
+        try:
+            for name, (fn, nbytes) in epi_cases.items():
+                res[name + "[direct kernel]"] = time_case(name, fn, nbytes)
+        finally:
+            native.check(L.ed_set_epilogue_mode(native.EPILOGUE_AUTO))
     return res, peak, how
 
 
@@ -341,12 +396,16 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=list(WORKLOADS))
     ap.add_argument("--no-extras", action="store_true", help="skip roofline / cpu_baseline / e2e legs (debug)")
     ap.add_argument("--roofline-only", action="store_true", help="only the L2-exceeding kernel roofline table (debug / ncu)")
+    ap.add_argument("--roofline-cases", default="", help="comma-separated kernel_rooflines case names (with --roofline-only)")
+    ap.add_argument("--roofline-iters", type=int, default=10)
+    ap.add_argument("--roofline-warm", type=int, default=3)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
     if args.roofline_only:
         torch.cuda.set_device(0)
-        roof, peak, how = kernel_rooflines(torch.device("cuda", 0))
+        only = [c for c in args.roofline_cases.split(",") if c] or None
+        roof, peak, how = kernel_rooflines(torch.device("cuda", 0), iters=args.roofline_iters, warm=args.roofline_warm, only=only)
         print(json.dumps({"roofline_all": roof, "peak": peak, "peak_source": how}))
         return
 
@@ -450,8 +509,8 @@ def main():
             line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": roof[dom]["GB/s"], "peak": peak,
                                 "unit": "GB/s", "frac": roof[dom]["frac"],
                                 # DRAM read+write bytes of one launch at exactly these sizes, from the committed
-                                # `ncu --set full` capture profiles/r1_epi_renoise3.ncu-rep (1.10 x algorithmic bytes)
-                                "traffic": 1.2598e9, "algorithmic_bytes": roof[dom]["algorithmic_MB"] * 1e6,
+                                # `ncu --set full` capture named in profiles/traffic.json
+                                "traffic": ncu_traffic(dom), "algorithmic_bytes": roof[dom]["algorithmic_MB"] * 1e6,
                                 "peak_source": how,
                                 "sizes": "B=96 SDXL 1024x2048 latents per launch (L2-exceeding); in-pipeline launches are "
                                          "L2-resident and latency-bound, see kernels_in_step"}

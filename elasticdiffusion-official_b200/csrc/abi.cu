@@ -23,17 +23,26 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 int encode_tmap_3d_f32(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0,
                        uint32_t b1, uint32_t b2) {
+  return encode_tmap_3d(map, base, ED_F32, d0, d1, d2, b0, b1, b2);
+}
+
+int encode_tmap_3d(CUtensorMap* map, const void* base, int dtype, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0,
+                   uint32_t b1, uint32_t b2) {
+  const uint64_t es = dtype == ED_F32 ? 4 : 2;
+  const CUtensorMapDataType dt = dtype == ED_F32   ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : dtype == ED_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                   : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   // TMA constraints: 16-byte aligned base and strides, inner box a multiple of 16 bytes, box dims <= 256.
-  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((d0 * 4) & 15) || ((b0 * 4) & 15) || b0 > 256 || b1 > 256 ||
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((d0 * es) & 15) || ((b0 * es) & 15) || b0 > 256 || b1 > 256 ||
       b2 > 256 || b0 == 0 || b1 == 0 || b2 == 0)
     return ED_ERR_UNSUPPORTED;
   auto fn = get_encode_fn();
   if (!fn) return ED_ERR_NO_DEVICE;
   cuuint64_t dims[3] = {d0, d1, d2};
-  cuuint64_t strides[2] = {d0 * 4, d0 * d1 * 4};
+  cuuint64_t strides[2] = {d0 * es, d0 * d1 * es};
   cuuint32_t box[3] = {b0, b1, b2};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = fn(map, dt, 3, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

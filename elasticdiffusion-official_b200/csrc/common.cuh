@@ -4,9 +4,16 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "elastic_b200.h"
+
+// spellings that differ between the nvcc build and the host emulation of the staged epilogue (tests/emu/emu_shim.h)
+#define ED_DEVICE __device__ __forceinline__
+#define ED_TMAP CUtensorMap
+#define ED_DYN_SMEM(name) extern __shared__ __align__(128) uint8_t name[]
 
 namespace ed {
 
@@ -95,6 +102,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
       "r"(phase)
       : "memory");
 }
+// bounded variant for kernels where every thread of the CTA waits: a transaction count that never completes (a bug) ends
+// in a trap (= CUDA error at the next sync) after ~2^24 polls instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t phase) {
+  uint32_t done = 0;
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+    if (done) return;
+  }
+  asm volatile("trap;");
+}
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2,
                                             uint64_t* bar) {
   asm volatile(
@@ -122,5 +148,8 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 // 3-D fp32 tensor (d0 fastest).  Returns ED_OK / ED_ERR_UNSUPPORTED (alignment) / ED_ERR_CUDA.
 int encode_tmap_3d_f32(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0,
                        uint32_t b1, uint32_t b2);
+// same for any ed_dtype element type (fp32 / fp16 / bf16)
+int encode_tmap_3d(CUtensorMap* map, const void* base, int dtype, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0,
+                   uint32_t b1, uint32_t b2);
 
 }  // namespace ed

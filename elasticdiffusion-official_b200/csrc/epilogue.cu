@@ -9,7 +9,9 @@
 //
 // Arithmetic uses explicit round-to-nearest intrinsics (no FMA contraction) in the reference's operation order, so
 // that with identical UNet outputs the result is bit-identical to eager fp32 PyTorch on CPU.
-#include "common.cuh"
+#include <atomic>
+
+#include "epilogue_staged.cuh"
 
 #ifndef ED_EPI_MINB
 #define ED_EPI_MINB 2   // CTAs of 256 threads per SM the epilogue is compiled for (register cap 65536 / (256 * MINB))
@@ -17,19 +19,9 @@
 
 namespace ed {
 
-struct EpiArgs {
-  ed_plan_t P;
-  const ed_step_params_t* prm;
-  const float* latent;
-  const void* unet_out;
-  const void* const* peers;   // multi-GPU: device array of `world` base pointers (peer-mapped), sample s lives on rank
-  int world, per;             //   s / per at local index s % per; NULL: all samples in unet_out
-  const uint8_t* idx;
-  const uint8_t* owner;
-  const float* noise;
-  float* out_latent;
-  float* out_x0;
-};
+// EpiArgs: epilogue_staged.cuh
+
+static std::atomic<int> g_epilogue_mode{ED_EPILOGUE_AUTO};
 
 // Which resampling iteration wrote target_direction[y, x] last (ed:637: every iteration overwrites where its mask is
 // set; ed:643-644: what is still NaN after the last iteration takes the last iteration's value).  All idx bytes are
@@ -140,7 +132,7 @@ __global__ void __launch_bounds__(256, ED_EPI_MINB) wave_epilogue_kernel(const E
   if (xv * VEC >= P.W || y >= P.H) return;
   const ed_step_params_t& S = *A.prm;
   const OT* __restrict__ out = static_cast<const OT*>(A.unet_out);
-  const int R1 = S.R1;
+  const int R1 = A.R1;
   const int flags = S.flags;
   const bool fp16sem = (flags & ED_FLAG_FP16_SEM) != 0;
   const bool rrg = (flags & ED_FLAG_RRG) != 0;
@@ -376,6 +368,38 @@ static int epi_grid(long long threads) {
 
 using namespace ed;
 
+// Tile-staged kernel (epilogue_staged.cuh).  ED_ERR_UNSUPPORTED: shape / alignment outside what it handles - the caller
+// then runs the direct kernel.
+template <typename OT>
+static int launch_staged(const EpiArgs& A, int out_dtype, cudaStream_t stream) {
+  const ed_plan_t& P = A.P;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    ED_CUDA_CHECK(cudaGetDevice(&dev));
+    ED_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  StagedCfg cfg = staged_config(P, A.R1, (int)sizeof(OT), sms);
+  if (!cfg.ok) return ED_ERR_UNSUPPORTED;
+  const long long n_samples = 2LL * P.B * A.R1 + (long long)P.nv * P.B;
+  CUtensorMap tm;
+  // all samples of the wave as (dW, dH, samples * C) planes; box = cells x rows x C channels of one sample
+  int rc = encode_tmap_3d(&tm, A.unet_out, out_dtype, (uint64_t)P.dW, (uint64_t)P.dH, (uint64_t)n_samples * P.C,
+                          (uint32_t)cfg.g.bw, (uint32_t)cfg.g.bh, (uint32_t)P.C);
+  if (rc != ED_OK) return rc;
+  cfg.g.vec_views = 1;   // encode_tmap_3d checked the 16-byte alignment of unet_out; dH*dW*sizeof(OT) is a multiple of 16
+  static bool attr_set = false;   // one flag per template instantiation
+  if (!attr_set) {
+    ED_CUDA_CHECK(cudaFuncSetAttribute(wave_epilogue_staged_kernel<OT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  const dim3 block(cfg.g.bx, cfg.g.by), grid(cfg.grid_x, cfg.grid_y, cfg.grid_z);
+  wave_epilogue_staged_kernel<OT><<<grid, block, cfg.smem, stream>>>(tm, A, cfg.g);
+  ED_LAUNCH_CHECK();
+  return ED_OK;
+}
+
+
 extern "C" {
 
 int ed_owner_map(const ed_plan_t* plan, int R1, const uint8_t* idx, uint8_t* owner, void* stream_) {
@@ -388,11 +412,12 @@ int ed_owner_map(const ed_plan_t* plan, int R1, const uint8_t* idx, uint8_t* own
   return ED_OK;
 }
 
-static int launch_epilogue(const ed_plan_t* plan, const ed_step_params_t* d_params, const float* latent,
+static int launch_epilogue(const ed_plan_t* plan, const ed_step_params_t* d_params, int R1, const float* latent,
                            const void* unet_out, const void* const* peers, int world, int per, int out_dtype,
                            const uint8_t* idx, const uint8_t* owner, const float* noise, float* out_latent, float* out_x0,
                            void* stream_) {
   if (!plan || !d_params || !latent || (!unet_out && !peers) || !idx || !owner || !out_latent) return ED_ERR_INVALID;
+  if (R1 <= 0 || R1 > 255) return ED_ERR_INVALID;
   if (peers && (world <= 0 || per <= 0)) return ED_ERR_INVALID;
   const ed_plan_t& P = *plan;
   if (!P.mrow_lo || !P.mrow_n || !P.mcol_lo || !P.mcol_n || !P.up_row || !P.up_col || !P.down_row || !P.down_col ||
@@ -403,10 +428,24 @@ static int launch_epilogue(const ed_plan_t* plan, const ed_step_params_t* d_para
   // channels per thread: 4 when the batch alone fills the GPU, 1 (channels spread over gridDim.z) for small batches
   const int cpt = (P.C % 4 == 0 && P.B >= 8 && !peers) ? 4 : 1;
   const int c_split = P.C / cpt;
-  EpiArgs A{P, d_params, latent, unet_out, peers, world, per, idx, owner, noise, out_latent, out_x0};
+  EpiArgs A{P, d_params, latent, unet_out, peers, world, per, idx, owner, noise, out_latent, out_x0, R1};
   auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const bool vec = (P.W % 4 == 0) && aligned(latent) && aligned(out_latent) && (!out_x0 || aligned(out_x0)) &&
                    (!noise || aligned(noise));
+  const int mode = g_epilogue_mode.load();
+  if (mode != ED_EPILOGUE_DIRECT) {
+    int rc = ED_ERR_UNSUPPORTED;
+    if (!peers && vec && (reinterpret_cast<uintptr_t>(owner) & 3) == 0) {
+      switch (out_dtype) {
+        case ED_F32: rc = launch_staged<float>(A, out_dtype, stream); break;
+        case ED_F16: rc = launch_staged<__half>(A, out_dtype, stream); break;
+        case ED_BF16: rc = launch_staged<__nv_bfloat16>(A, out_dtype, stream); break;
+        default: return ED_ERR_INVALID;
+      }
+    }
+    if (rc != ED_ERR_UNSUPPORTED) return rc;
+    if (mode == ED_EPILOGUE_STAGED) return ED_ERR_UNSUPPORTED;   // forced: do not silently take the other kernel
+  }
   const int wv = vec ? P.W / 4 : P.W;
   int bx = 32;
   while (bx > 1 && bx / 2 >= wv) bx /= 2;                 // narrow rows: fewer idle lanes
@@ -432,18 +471,24 @@ static int launch_epilogue(const ed_plan_t* plan, const ed_step_params_t* d_para
   return ED_OK;
 }
 
-int ed_wave_epilogue(const ed_plan_t* plan, const ed_step_params_t* d_params, const float* latent, const void* unet_out,
-                     int out_dtype, const uint8_t* idx, const uint8_t* owner, const float* noise, float* out_latent,
-                     float* out_x0, void* stream_) {
-  return launch_epilogue(plan, d_params, latent, unet_out, nullptr, 0, 0, out_dtype, idx, owner, noise, out_latent, out_x0,
-                         stream_);
+int ed_wave_epilogue(const ed_plan_t* plan, const ed_step_params_t* d_params, int R1, const float* latent,
+                     const void* unet_out, int out_dtype, const uint8_t* idx, const uint8_t* owner, const float* noise,
+                     float* out_latent, float* out_x0, void* stream_) {
+  return launch_epilogue(plan, d_params, R1, latent, unet_out, nullptr, 0, 0, out_dtype, idx, owner, noise, out_latent,
+                         out_x0, stream_);
 }
 
-int ed_wave_epilogue_peer(const ed_plan_t* plan, const ed_step_params_t* d_params, const float* latent,
+int ed_wave_epilogue_peer(const ed_plan_t* plan, const ed_step_params_t* d_params, int R1, const float* latent,
                           const void* const* d_peer_out, int world, int per, int out_dtype, const uint8_t* idx,
                           const uint8_t* owner, const float* noise, float* out_latent, float* out_x0, void* stream_) {
-  return launch_epilogue(plan, d_params, latent, nullptr, d_peer_out, world, per, out_dtype, idx, owner, noise, out_latent,
-                         out_x0, stream_);
+  return launch_epilogue(plan, d_params, R1, latent, nullptr, d_peer_out, world, per, out_dtype, idx, owner, noise,
+                         out_latent, out_x0, stream_);
+}
+
+int ed_set_epilogue_mode(int mode) {
+  if (mode != ED_EPILOGUE_AUTO && mode != ED_EPILOGUE_DIRECT && mode != ED_EPILOGUE_STAGED) return ED_ERR_INVALID;
+  g_epilogue_mode.store(mode);
+  return ED_OK;
 }
 
 int ed_renoise(const ed_step_params_t* d_params, const float* x, const float* noise, float* out, int64_t numel,

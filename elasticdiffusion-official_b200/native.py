@@ -17,6 +17,8 @@ SOURCES = ["abi.cu", "gather.cu", "epilogue.cu", "tiles.cu"]
 ED_MAX_RENOISE = 1000
 ED_F32, ED_F16, ED_BF16 = 0, 1, 2
 FLAG_RENOISE, FLAG_RRG, FLAG_FP16_SEM = 1, 2, 4
+EPILOGUE_AUTO, EPILOGUE_DIRECT, EPILOGUE_STAGED = 0, 1, 2
+ABI_VERSION = 3
 
 
 class NativeError(RuntimeError):
@@ -60,10 +62,11 @@ EXPORTS = {
                                         C.c_void_p, C.c_int, C.c_void_p]),
     "ed_pad_views": (C.c_int, [C.POINTER(Plan), C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "ed_owner_map": (C.c_int, [C.POINTER(Plan), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "ed_wave_epilogue": (C.c_int, [C.POINTER(Plan), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+    "ed_wave_epilogue": (C.c_int, [C.POINTER(Plan), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "ed_wave_epilogue_peer": (C.c_int, [C.POINTER(Plan), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
-                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ed_wave_epilogue_peer": (C.c_int, [C.POINTER(Plan), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                        C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ed_set_epilogue_mode": (C.c_int, [C.c_int]),
     "ed_renoise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ed_gather_cond": (C.c_int, [C.POINTER(Plan), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_int, C.c_void_p]),
@@ -78,7 +81,8 @@ _lib = None
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/*.cu into libelastic_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
     srcs = [os.path.join(_HERE, "csrc", s) for s in SOURCES]
-    deps = srcs + [os.path.join(_HERE, "csrc", "common.cuh"), os.path.join(_ROOT, "include", "elastic_b200.h")]
+    deps = srcs + [os.path.join(_HERE, "csrc", "common.cuh"), os.path.join(_HERE, "csrc", "epilogue_staged.cuh"),
+                   os.path.join(_ROOT, "include", "elastic_b200.h")]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
@@ -106,7 +110,7 @@ def lib():
         for name, (res, args) in EXPORTS.items():
             fn = getattr(l, name)           # AttributeError if the ABI lost a symbol
             fn.restype, fn.argtypes = res, args
-        if l.ed_abi_version() != 2:
+        if l.ed_abi_version() != ABI_VERSION:
             raise NativeError("libelastic_b200 ABI version mismatch")
         _lib = l
     return _lib

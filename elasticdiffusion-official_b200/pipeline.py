@@ -817,11 +817,11 @@ class ElasticDiffusion(nn.Module):
             tag = "+renoise" if prm.flags & 1 else "+rrg" if prm.flags & 2 else ""
             if isinstance(out, PeerOut):
                 launch("ed_wave_epilogue_peer" + tag, L.ed_wave_epilogue_peer, ctypes.byref(plan),
-                       native.ptr(d_params[slot]), native.ptr(x_in), native.ptr(out.ptrs), out.world, out.per,
+                       native.ptr(d_params[slot]), R1, native.ptr(x_in), native.ptr(out.ptrs), out.world, out.per,
                        native.dtype_code(out.dtype), native.ptr(idx_dev), native.ptr(owner), native.ptr(noise_buf),
                        native.ptr(x_out), native.ptr(x0_out), st)
             else:
-                launch("ed_wave_epilogue" + tag, L.ed_wave_epilogue, ctypes.byref(plan), native.ptr(d_params[slot]),
+                launch("ed_wave_epilogue" + tag, L.ed_wave_epilogue, ctypes.byref(plan), native.ptr(d_params[slot]), R1,
                        native.ptr(x_in), native.ptr(out), native.dtype_code(out.dtype), native.ptr(idx_dev),
                        native.ptr(owner), native.ptr(noise_buf), native.ptr(x_out), native.ptr(x0_out), st)
             return out

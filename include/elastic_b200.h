@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ED_ABI_VERSION 2
+#define ED_ABI_VERSION 3
 #define ED_MAX_RENOISE 1000
 
 typedef enum {
@@ -145,13 +145,23 @@ int ed_owner_map(const ed_plan_t* plan, int R1, const uint8_t* idx, uint8_t* own
  *   - eps = uncond + g*direction, DDIM x0 / x_prev          ed:1031-1035, 1053-1056 (+ diffusers step)
  *   - flags & ED_FLAG_RENOISE: undo_step                    ed:692-704 (noise = n_renoise torch-drawn tensors)
  *   - flags & ED_FLAG_RRG: reduced-resolution guidance      ed:886-940 and global_latent = nxt + cascade ed:1078
+ * R1        resampling iterations of the wave (= d_params->R1; the host needs it to size the launch)
  * unet_out  (n_samples, C, dH, dW) of dtype out_dtype in the wave sample layout
  * owner     (H*W) uint8 from ed_owner_map for the same idx
  * noise     [n_renoise][B*C*H*W] fp32 or NULL
- * out_latent / out_x0 fp32 (B,C,H,W); out_x0 may be NULL. */
-int ed_wave_epilogue(const ed_plan_t* plan, const ed_step_params_t* d_params, const float* latent,
+ * out_latent / out_x0 fp32 (B,C,H,W); out_x0 may be NULL.
+ * Two kernels implement it (bit-identical results): the tile-staged one (a CTA pulls the low-res rectangle of all 2*R1
+ * global-pass outputs behind its latent tile into shared memory with TMA box loads, then picks per pixel from shared
+ * memory) whenever C == 4, W % 4 == 0, 16-byte aligned buffers and the boxes fit in shared memory; otherwise the direct
+ * kernel (scattered read-only loads). */
+int ed_wave_epilogue(const ed_plan_t* plan, const ed_step_params_t* d_params, int R1, const float* latent,
                      const void* unet_out, int out_dtype, const uint8_t* idx, const uint8_t* owner,
                      const float* noise, float* out_latent, float* out_x0, void* stream);
+
+/* Kernel selection of ed_wave_epilogue, process-wide (tests / A-B measurements): AUTO as described above, DIRECT never
+ * stages, STAGED returns ED_ERR_UNSUPPORTED instead of falling back. */
+typedef enum { ED_EPILOGUE_AUTO = 0, ED_EPILOGUE_DIRECT = 1, ED_EPILOGUE_STAGED = 2 } ed_epilogue_mode;
+int ed_set_epilogue_mode(int mode);
 
 /* ---- C1: the same epilogue fused with the multi-GPU exchange ---------------------------------
  * With wave samples sharded over `world` ranks (rank r holds samples [r*per, (r+1)*per) of the wave layout in its own
@@ -159,7 +169,7 @@ int ed_wave_epilogue(const ed_plan_t* plan, const ed_step_params_t* d_params, co
  * into this process (symmetric memory / CUDA IPC), and the kernel reads every sample it needs straight from its owner
  * over NVLink (P2P ld.global).  The caller orders "all ranks finished their UNet" before the launch (device-side
  * symmetric-memory barrier).  Every rank runs the (replicated, microsecond) epilogue itself. */
-int ed_wave_epilogue_peer(const ed_plan_t* plan, const ed_step_params_t* d_params, const float* latent,
+int ed_wave_epilogue_peer(const ed_plan_t* plan, const ed_step_params_t* d_params, int R1, const float* latent,
                           const void* const* d_peer_out, int world, int per, int out_dtype, const uint8_t* idx,
                           const uint8_t* owner, const float* noise, float* out_latent, float* out_x0, void* stream);
 

@@ -49,7 +49,10 @@ GEOS = [(1, 128, 256, 128, (64, 128), 64),      # cfg3  SDXL 1024x2048
         (1, 80, 112, 64, (45, 64), 32),         # ragged SD
         (1, 96, 128, 64, (48, 64), 32),
         (1, 128, 256, 128, (64, 128), 32),      # patch_size=32: overlapping last windows
-        (2, 96, 256, 128, (48, 128), 64)]       # window collapse: views 96 rows < native 128 -> ed_pad_views, v_tp offsets
+        (2, 96, 256, 128, (48, 128), 64),       # window collapse: views 96 rows < native 128 -> ed_pad_views, v_tp offsets
+        (1, 128, 256, 64, (32, 64), 32),        # downsample factor 4 (SD 1024x2048; the reference's "factor > 2" TODO path)
+        (1, 192, 192, 64, (64, 64), 32),        # downsample factor 3
+        (1, 72, 100, 64, (36, 50), 32)]         # W % 4 == 0 but unaligned low-res offsets (g_lp = 7): TMA boxes at odd coordinates
 
 
 def build(cfg):
@@ -84,14 +87,25 @@ def test_gather_kernels_match_spec(cfg, dtype):
     assert torch.equal(canvas, want)
 
 
+@pytest.fixture
+def epilogue_kernel(request):
+    """direct = scattered-load kernel, staged = TMA tile-staged kernel (forced: an unsupported shape is an error, not a
+    silent fall-back to the other kernel)."""
+    L = native.lib()
+    native.check(L.ed_set_epilogue_mode({"direct": native.EPILOGUE_DIRECT, "staged": native.EPILOGUE_STAGED}[request.param]))
+    yield request.param
+    native.check(L.ed_set_epilogue_mode(native.EPILOGUE_AUTO))
+
+
 @pytest.mark.parametrize("cfg", GEOS)
 @pytest.mark.parametrize("mode", ["plain", "renoise", "rrg"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
-def test_wave_epilogue_matches_spec(cfg, mode, dtype):
+@pytest.mark.parametrize("epilogue_kernel", ["direct", "staged"], indirect=True)
+def test_wave_epilogue_matches_spec(cfg, mode, dtype, epilogue_kernel, R1=None):
     L = native.lib()
     geo = build(cfg)
     plan, keep = upload(geo)
-    R1 = 1 if (mode == "rrg" and cfg[0] == 2) else 4
+    R1 = R1 or (1 if (mode == "rrg" and cfg[0] == 2) else 4)
     torch.manual_seed(1)
     x = torch.randn(geo.B, geo.C, geo.H, geo.W, device=DEV)
     idx = rand_idx(R1, geo.lh * geo.lw, 5)
@@ -121,13 +135,60 @@ def test_wave_epilogue_matches_spec(cfg, mode, dtype):
     owner = torch.full((geo.H * geo.W,), 255, dtype=torch.uint8, device=DEV)
     native.check(L.ed_owner_map(ctypes.byref(plan), R1, native.ptr(idx), native.ptr(owner), st))
     assert torch.equal(owner.view(geo.H, geo.W).long(), ws.owner_map(geo, R1, idx, DEV))
-    native.check(L.ed_wave_epilogue(ctypes.byref(plan), native.ptr(d_prm), native.ptr(x), native.ptr(out),
+    native.check(L.ed_wave_epilogue(ctypes.byref(plan), native.ptr(d_prm), R1, native.ptr(x), native.ptr(out),
                                     native.dtype_code(dtype), native.ptr(idx), native.ptr(owner), native.ptr(noise),
                                     native.ptr(y), native.ptr(x0), st))
     torch.cuda.synchronize()
     want, want_x0 = ws.spec_epilogue(geo, prm, x, out, idx, noise)
     assert torch.equal(x0, want_x0), f"x0 max diff {(x0 - want_x0).abs().max().item():.3e}"
     assert torch.equal(y, want), f"latent max diff {(y - want).abs().max().item():.3e}"
+
+
+@pytest.mark.parametrize("cfg,R1,dtype", [(GEOS[0], 8, torch.bfloat16),      # cfg3 wave 1
+                                          (GEOS[1], 21, torch.float32),      # signature default resampling_steps = 20, fp32 boxes
+                                          (GEOS[1], 21, torch.float16),
+                                          (GEOS[3], 8, torch.float16),       # cfg4
+                                          ((16, 128, 256, 128, (64, 128), 64), 8, torch.bfloat16)])   # batch large enough for the 256-thread CTA
+@pytest.mark.parametrize("mode", ["renoise", "rrg"])
+@pytest.mark.parametrize("epilogue_kernel", ["staged"], indirect=True)
+def test_staged_epilogue_many_iterations_and_large_ctas(cfg, R1, dtype, mode, epilogue_kernel):
+    test_wave_epilogue_matches_spec(cfg, mode, dtype, epilogue_kernel, R1=R1)
+
+
+def test_auto_mode_takes_the_direct_kernel_where_staging_does_not_apply():
+    """W % 4 != 0 is outside the staged kernel's domain: forced staging must say so, AUTO must still produce the result."""
+    L = native.lib()
+    cfg = (1, 128, 250, 128, (64, 125), 64)
+    geo = build(cfg)
+    plan, keep = upload(geo)
+    R1 = 2
+    x = torch.randn(1, 4, 128, 250, device=DEV)
+    idx = rand_idx(R1, geo.lh * geo.lw, 5)
+    n = 2 * R1 + geo.nv
+    out = torch.randn(n, 4, 128, 128, device=DEV)
+    prm = dict(guidance=7.5, sqrt_beta_t=0.9637, sqrt_alpha_t=0.2669, sqrt_alpha_prev=0.3316, sqrt_dir=0.9434,
+               rrg_weight=0.0, rrg_norm=0.0, flags=0, n_renoise=0, R1=R1)
+    sp = native.StepParams(**prm)
+    for k in ("guidance", "sqrt_beta_t", "sqrt_alpha_t", "sqrt_alpha_prev", "sqrt_dir"):
+        prm[k] = float(getattr(sp, k))
+    d_prm = torch.empty(ctypes.sizeof(native.StepParams), dtype=torch.uint8, device=DEV)
+    st = native.stream_handle()
+    native.check(L.ed_upload_step_params(native.ptr(d_prm), ctypes.byref(sp), st))
+    owner = torch.empty(geo.H * geo.W, dtype=torch.uint8, device=DEV)
+    native.check(L.ed_owner_map(ctypes.byref(plan), R1, native.ptr(idx), native.ptr(owner), st))
+    y = torch.empty_like(x)
+    args = (ctypes.byref(plan), native.ptr(d_prm), R1, native.ptr(x), native.ptr(out), native.ED_F32, native.ptr(idx),
+            native.ptr(owner), None, native.ptr(y), None, st)
+    try:
+        native.check(L.ed_set_epilogue_mode(native.EPILOGUE_STAGED))
+        assert L.ed_wave_epilogue(*args) == -2          # ED_ERR_UNSUPPORTED
+    finally:
+        native.check(L.ed_set_epilogue_mode(native.EPILOGUE_AUTO))
+    native.check(L.ed_wave_epilogue(*args))
+    torch.cuda.synchronize()
+    want, _ = ws.spec_epilogue(geo, prm, x, out, idx, None)
+    assert torch.equal(y, want)
+    assert L.ed_set_epilogue_mode(7) == -1
 
 
 def test_renoise_kernel_matches_sequential_axpy_and_is_linear():

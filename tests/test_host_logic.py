@@ -26,7 +26,7 @@ def test_library_loads_and_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/elastic_b200.h but not exported"
     assert declared == set(native.EXPORTS), "ctypes binding and header disagree"
     L = native.lib()
-    assert L.ed_abi_version() == 2
+    assert L.ed_abi_version() == native.ABI_VERSION == 3
     assert L.ed_strerror(-2).decode().startswith("unsupported")
 
 
