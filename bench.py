@@ -197,7 +197,7 @@ def kernel_rooflines(device, B=96, out_dtype=torch.bfloat16, iters=10, warm=3, o
         "ed_wave_epilogue+renoise": (epi(0, R1, out, idx, owner, native.ptr(noise)),
                                      Lb + win * so + glob(R1, idx, owner, False) + H * W + n_re * Lb + Lb),
         # wave 2 of a repaint step while RRG is active (cfg3: one iteration) - the RRG launch of the BASELINE config
-        "ed_wave_epilogue+rrg(wave2,R1=1)": (epi(2, 1, out_w2, idx_w2, owner_w2, None),
+        "ed_wave_epilogue+rrg(wave2:R1=1)": (epi(2, 1, out_w2, idx_w2, owner_w2, None),
                                              Lb + win * so + glob(1, idx_w2, owner_w2, True) + H * W + cells + Lb),
         # repaint_sampling=False: RRG in the R1 = 8 wave
         "ed_wave_epilogue+rrg": (epi(1, R1, out, idx, owner, None),

@@ -9,6 +9,8 @@
 //
 // Arithmetic uses explicit round-to-nearest intrinsics (no FMA contraction) in the reference's operation order, so
 // that with identical UNet outputs the result is bit-identical to eager fp32 PyTorch on CPU.
+#include <stdlib.h>
+
 #include <atomic>
 
 #include "epilogue_staged.cuh"
@@ -379,7 +381,8 @@ static int launch_staged(const EpiArgs& A, int out_dtype, cudaStream_t stream) {
     ED_CUDA_CHECK(cudaGetDevice(&dev));
     ED_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  StagedCfg cfg = staged_config(P, A.R1, (int)sizeof(OT), sms);
+  static const int origin = getenv("ED_STAGED_ORIGIN") ? atoi(getenv("ED_STAGED_ORIGIN")) : (ED_BOX_ALIGN | ED_BOX_CLAMP);
+  StagedCfg cfg = staged_config(P, A.R1, (int)sizeof(OT), sms, origin);
   if (!cfg.ok) return ED_ERR_UNSUPPORTED;
   const long long n_samples = 2LL * P.B * A.R1 + (long long)P.nv * P.B;
   CUtensorMap tm;

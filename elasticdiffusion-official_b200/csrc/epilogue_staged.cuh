@@ -46,7 +46,11 @@ struct StagedGeom {
   int bw, bh;             // TMA box in low-res cells: columns (padded to 16 bytes), rows
   unsigned stage_bytes;   // shared-memory stride between the boxes of consecutive samples (multiple of 128)
   int vec_views;          // unet_out is 16-byte aligned: 4 consecutive view elements may be loaded with one instruction
+  int origin;             // box origin policy, ED_BOX_*
+  int col_align;          // elements per 16 bytes of the UNet output dtype
 };
+#define ED_BOX_ALIGN 1   // box starts at a 16-byte aligned canvas column
+#define ED_BOX_CLAMP 2   // box shifted back inside the canvas plane: no out-of-bounds (zero-filled) part
 
 struct StagedCfg {
   bool ok;
@@ -58,7 +62,8 @@ struct StagedCfg {
 // Largest number of source indices that nearest-upsampling (src = min(floor(dst * in/out), in-1), float scale like
 // F.interpolate, ed:876) reads for `tile` consecutive outputs starting at a multiple of `tile`.  An estimate only: the
 // kernel re-derives the rectangle from the plan's tables and falls back to global loads where a tile needs more.
-static inline int nearest_span_max(int n_out, int n_in, int tile) {
+// `offset` / `align`: the span is measured from the source index + offset rounded down to a multiple of `align`.
+static inline int nearest_span_max(int n_out, int n_in, int tile, int offset = 0, int align = 1) {
   const float s = (float)n_in / (float)n_out;
   int best = 1;
   for (int o0 = 0; o0 < n_out; o0 += tile) {
@@ -66,6 +71,7 @@ static inline int nearest_span_max(int n_out, int n_in, int tile) {
     int a = (int)floorf((float)o0 * s), b = (int)floorf((float)o1 * s);
     a = a < n_in - 1 ? a : n_in - 1;
     b = b < n_in - 1 ? b : n_in - 1;
+    a = (a + offset) / align * align - offset;
     best = b - a + 1 > best ? b - a + 1 : best;
   }
   return best;
@@ -74,7 +80,7 @@ static inline int nearest_span_max(int n_out, int n_in, int tile) {
 // so = bytes per UNet output element.  Preference: the largest CTA whose boxes fit twice per SM (<= 100 KB) and whose grid
 // fills the GPU at least twice; otherwise the smallest CTA that fits (more CTAs for small batches); otherwise one CTA
 // per SM (<= 200 KB); otherwise not applicable (the direct kernel runs).
-static inline StagedCfg staged_config(const ed_plan_t& P, int R1, int so, int sms) {
+static inline StagedCfg staged_config(const ed_plan_t& P, int R1, int so, int sms, int origin = ED_BOX_ALIGN | ED_BOX_CLAMP) {
   StagedCfg best{};
   if (P.C != 4 || (P.W & 3) || R1 <= 0 || P.B > 65535 || P.B <= 0) return best;
   const int wv = P.W / 4;
@@ -85,12 +91,12 @@ static inline StagedCfg staged_config(const ed_plan_t& P, int R1, int so, int sm
   for (int threads = 256; threads >= 64; threads >>= 1) {
     const int by = threads / bx;
     if (by < 1) break;
-    int bw = nearest_span_max(P.W, P.lw, bx * 4);
+    int bw = nearest_span_max(P.W, P.lw, bx * 4, P.g_lp, (origin & ED_BOX_ALIGN) ? align : 1);
     bw = (bw + align - 1) / align * align;
     const int bh = nearest_span_max(P.H, P.lh, by);
     if (bw > 256 || bh > 256) continue;
     const unsigned stage = ((unsigned)(bw * bh * P.C * so) + 127u) & ~127u;
-    const size_t smem = (size_t)R1 * 2 * stage;
+    const size_t smem = (size_t)R1 * 2 * stage + (size_t)bw * bh * P.C * 4;   // boxes + the RRG low-res reference
     if (smem > 200 * 1024) continue;
     const int gx = (P.W + bx * 4 - 1) / (bx * 4), gy = (P.H + by - 1) / by;
     const long long ctas = (long long)gx * gy * P.B;
@@ -98,7 +104,7 @@ static inline StagedCfg staged_config(const ed_plan_t& P, int R1, int so, int sm
     // rank 3 stops the search (largest CTA wins); among rank <= 2 the later (smaller) CTA wins ties
     if (rank >= best_rank) {
       best.ok = true;
-      best.g = StagedGeom{bx, by, bw, bh, stage, 0};
+      best.g = StagedGeom{bx, by, bw, bh, stage, 0, origin, align};
       best.smem = smem;
       best.grid_x = gx;
       best.grid_y = gy;
@@ -185,7 +191,15 @@ __global__ void __launch_bounds__(256, 2) wave_epilogue_staged_kernel(const __gr
   // low-res cells nearest-upsampling reads for this tile (ed:636); the tables are non-decreasing
   const int rlo = __ldg(P.up_row + Y0), rhi = __ldg(P.up_row + Y1 - 1);
   const int clo = __ldg(P.up_col + X0), chi = __ldg(P.up_col + X1 - 1);
-  const bool staged = (rhi - rlo < G.bh) && (chi - clo < G.bw);   // CTA-uniform; false: this tile reads global memory
+  // box origin in canvas coordinates (the low-res latent sits at (g_tp, g_lp) inside a canvas plane, ed:405-406)
+  int bx0 = P.g_lp + clo, by0 = P.g_tp + rlo;
+  if (G.origin & ED_BOX_ALIGN) bx0 = bx0 / G.col_align * G.col_align;
+  if (G.origin & ED_BOX_CLAMP) {
+    if (bx0 + G.bw > P.dW && G.bw <= P.dW) bx0 = P.dW - G.bw;
+    if (by0 + G.bh > P.dH && G.bh <= P.dH) by0 = P.dH - G.bh;
+  }
+  const int rb = by0 - P.g_tp, cb = bx0 - P.g_lp;   // box origin in low-res cell coordinates (<= rlo, clo)
+  const bool staged = (rhi - rb < G.bh) && (chi - cb < G.bw);   // CTA-uniform; false: this tile reads global memory
   if (tid == 0) {
     mbar_init(&bar, 1);
     fence_mbar_init();
@@ -195,10 +209,14 @@ __global__ void __launch_bounds__(256, 2) wave_epilogue_staged_kernel(const __gr
     const unsigned box_bytes = (unsigned)(G.bw * G.bh * P.C) * (unsigned)sizeof(OT);
     mbar_expect_tx(&bar, 2u * (unsigned)R1 * box_bytes);
     for (int ks = 0; ks < 2 * R1; ++ks)   // sample (k, s, b) = (2k + s) * B + b; planes of a sample are its C channels
-      tma_load_3d(smem_raw + (size_t)ks * G.stage_bytes, &tm, P.g_lp + clo, P.g_tp + rlo, (ks * P.B + b) * P.C, &bar);
+      tma_load_3d(smem_raw + (size_t)ks * G.stage_bytes, &tm, bx0, by0, (ks * P.B + b) * P.C, &bar);
   }
-  const int x = X0 + (int)threadIdx.x * 4, y = Y0 + (int)threadIdx.y;
-  if (x >= P.W || y >= P.H) return;   // thread (0,0) of every CTA is active and waits for the boxes below
+  // threads beyond the latent's edge stay alive (the per-cell RRG phase below uses every thread and a CTA barrier): they
+  // redo the work of the last valid position and skip the stores
+  int x = X0 + (int)threadIdx.x * 4, y = Y0 + (int)threadIdx.y;
+  const bool active = x < P.W && y < P.H;
+  x = x < P.W ? x : P.W - 4;
+  y = y < P.H ? y : P.H - 1;
 
   const OT* __restrict__ out = static_cast<const OT*>(A.unet_out);
   const int flags = S.flags;
@@ -267,9 +285,10 @@ __global__ void __launch_bounds__(256, 2) wave_epilogue_staged_kernel(const __gr
     }
   }
   // RRG references (ed:886-940): the pixel the LAST iteration picked for the pixel's low-res cell, and owner + cell of the
-  // full-res pixel nearest-DOWNsampling reads for that cell (ed:688)
-  int lat_off[4], kd[4], doff[4], r2[4], c2[4];
-  if (rrg) {
+  // full-res pixel nearest-DOWNsampling reads for that cell (ed:688).  Per pixel only on unstaged tiles; staged tiles
+  // compute the low-res reference once per cell (phase B1)
+  int lat_off[4], kd[4], doff[4];
+  if (rrg && !staged) {
     const int cells = P.lh * P.lw;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -279,9 +298,6 @@ __global__ void __launch_bounds__(256, 2) wave_epilogue_staged_kernel(const __gr
       const int2 d = __ldg(reinterpret_cast<const int2*>(P.cell_down) + cell);
       kd[e] = __ldg(A.owner + d.x);
       doff[e] = d.y;
-      const int rr = d.y / P.dW;
-      r2[e] = rr - P.g_tp;
-      c2[e] = d.y - rr * P.dW - P.g_lp;
     }
   }
 
@@ -290,6 +306,64 @@ __global__ void __launch_bounds__(256, 2) wave_epilogue_staged_kernel(const __gr
   const OT* sm = reinterpret_cast<const OT*>(smem_raw);
   const int stage_el = (int)(G.stage_bytes / sizeof(OT));
   const int plane_el = G.bh * G.bw;
+  // RRG low-res reference x0 (ed:909-921) of every cell behind the tile, channel-major in the box layout
+  float* rx0s = reinterpret_cast<float*>(smem_raw + (size_t)2 * R1 * G.stage_bytes);
+
+  // the reference's low-res DDIM x0 of one (cell, channel): xl = low-res latent of the last iteration, ul = its uncond
+  // score, (lun, lco) = uncond / cond scores behind downsampled_direction (ed:688, 909-921)
+  auto low_res_x0 = [&](float xl, float ul, float lun, float lco) -> float {
+    float dl = __fsub_rn(lco, lun);
+    if (fp16sem) dl = __half2float(__float2half_rn(dl));
+    float gl = __fmul_rn(g, dl);
+    float el, t1;
+    if (fp16sem) {
+      gl = __half2float(__float2half_rn(gl));
+      el = __half2float(__float2half_rn(__fadd_rn(ul, gl)));         // fp16 + fp16 (ed:918)
+      t1 = __half2float(__float2half_rn(__fmul_rn(sb, el)));         // 0-dim fp32 tensor * fp16 tensor -> fp16
+    } else {
+      el = __fadd_rn(ul, gl);
+      t1 = __fmul_rn(sb, el);
+    }
+    return __fdiv_rn(__fsub_rn(xl, t1), sa);                          // ed:920-921
+  };
+
+  // ---- phase B1 (staged tiles with RRG): the low-res reference depends on the CELL, not on the pixel - one evaluation per
+  // (cell, channel) of the tile's rectangle instead of one per pixel (4x fewer at ratio 1/2), shared through smem ---------
+  if (staged && rrg) {
+    const int nrc = chi - clo + 1, ncell = (rhi - rlo + 1) * nrc;
+    const int cells = P.lh * P.lw;
+    for (int i = tid; i < ncell; i += (int)(blockDim.x * blockDim.y)) {
+      const int rq = i / nrc;
+      const int r = rlo + rq, c = clo + (i - rq * nrc);
+      const int cell = r * P.lw + c;
+      const int pk = __ldg(A.idx + (long long)(R1 - 1) * cells + cell) & 3;
+      const int lo = __ldg(P.cell_cand + cell * 4 + pk);
+      const int2 d = __ldg(reinterpret_cast<const int2*>(P.cell_down) + cell);
+      const int kdn = __ldg(A.owner + d.x);
+      const int rr = d.y / P.dW;
+      const int rd = rr - P.g_tp, cd = d.y - rr * P.dW - P.g_lp;       // cell nearest-DOWNsampling reads (ed:688)
+      // inside the boxes at every exact ratio; general ratios may step outside at a tile border -> global load
+      const bool in_box = (unsigned)(rd - rb) < (unsigned)G.bh && (unsigned)(cd - cb) < (unsigned)G.bw;
+      ED_EMU_COUNT(in_box ? 2 : 3);
+      const int so = (r - rb) * G.bw + (c - cb), so2 = (rd - rb) * G.bw + (cd - cb);
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const float xl = __ldg(A.latent + ((long long)b * P.C + cc) * hw + lo);                 // ed:910
+        const float ul = to_f32<OT>(sm[(size_t)(2 * (R1 - 1)) * stage_el + cc * plane_el + so]);
+        float lun, lco;
+        if (in_box) {
+          lun = to_f32<OT>(sm[(size_t)(2 * kdn) * stage_el + cc * plane_el + so2]);
+          lco = to_f32<OT>(sm[(size_t)(2 * kdn + 1) * stage_el + cc * plane_el + so2]);
+        } else {
+          lun = ld_ro<OT>(sample((2 * kdn) * P.B + b) + cc * plane + d.y);
+          lco = ld_ro<OT>(sample((2 * kdn + 1) * P.B + b) + cc * plane + d.y);
+        }
+        rx0s[cc * plane_el + so] = low_res_x0(xl, ul, lun, lco);
+      }
+    }
+    __syncthreads();
+  }
+
   float res[4][4];
   auto finish = [&](auto staged_tag) {
     constexpr bool ST = decltype(staged_tag)::value;
@@ -303,7 +377,7 @@ __global__ void __launch_bounds__(256, 2) wave_epilogue_staged_kernel(const __gr
     float x0v[4][4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const int so = (ur - rlo) * G.bw + (pr[e].w - ur * P.lw - clo);
+      const int so = (ur - rb) * G.bw + (pr[e].w - ur * P.lw - cb);
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
         const float un = own_cell(own[e], 0, cc, so, pr[e].x), co = own_cell(own[e], 1, cc, so, pr[e].x);
@@ -317,47 +391,28 @@ __global__ void __launch_bounds__(256, 2) wave_epilogue_staged_kernel(const __gr
         res[cc][e] = __fadd_rn(__fmul_rn(sap, x0), __fmul_rn(sd, eps));              // x_{t-1}, eta = 0
       }
     }
-    if (A.out_x0) {
+    if (A.out_x0 && active) {
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc)
         *reinterpret_cast<float4*>(A.out_x0 + base0 + cc * hw) = make_float4(x0v[cc][0], x0v[cc][1], x0v[cc][2], x0v[cc][3]);
     }
     if (rrg) {
-      const int kl = R1 - 1;
       const float rrg_norm = S.rrg_norm, rrg_w = S.rrg_weight;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int so = (ur - rlo) * G.bw + (pr[e].w - ur * P.lw - clo);
-        // the cell nearest-DOWNsampling reads (ed:688) lies inside the boxes at every exact ratio; general ratios may step
-        // one cell outside at a tile border -> global load
-        const bool in_box = ST && (unsigned)(r2[e] - rlo) < (unsigned)G.bh && (unsigned)(c2[e] - clo) < (unsigned)G.bw;
-        const int so2 = (r2[e] - rlo) * G.bw + (c2[e] - clo);
-        ED_EMU_COUNT(in_box ? 2 : 3);
+        const int so = (ur - rb) * G.bw + (pr[e].w - ur * P.lw - cb);
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
-          const float xl = __ldg(A.latent + ((long long)b * P.C + cc) * hw + lat_off[e]);   // low-res latent, last iteration (ed:910)
-          const float ul = own_cell(kl, 0, cc, so, pr[e].x);                                  // its uncond score
-          float lun, lco;   // downsampled_direction = nearest-down of the filled full-res direction (ed:688)
-          if (in_box) {
-            lun = to_f32<OT>(sm[(size_t)(2 * kd[e]) * stage_el + cc * plane_el + so2]);
-            lco = to_f32<OT>(sm[(size_t)(2 * kd[e] + 1) * stage_el + cc * plane_el + so2]);
+          float rx0;
+          if constexpr (ST) {
+            rx0 = rx0s[cc * plane_el + so];
           } else {
-            lun = ld_ro<OT>(sample((2 * kd[e]) * P.B + b) + cc * plane + doff[e]);
-            lco = ld_ro<OT>(sample((2 * kd[e] + 1) * P.B + b) + cc * plane + doff[e]);
+            const float xl = __ldg(A.latent + ((long long)b * P.C + cc) * hw + lat_off[e]);
+            const float ul = own_cell(R1 - 1, 0, cc, so, pr[e].x);
+            const float lun = ld_ro<OT>(sample((2 * kd[e]) * P.B + b) + cc * plane + doff[e]);
+            const float lco = ld_ro<OT>(sample((2 * kd[e] + 1) * P.B + b) + cc * plane + doff[e]);
+            rx0 = low_res_x0(xl, ul, lun, lco);
           }
-          float dl = __fsub_rn(lco, lun);
-          if (fp16sem) dl = __half2float(__float2half_rn(dl));
-          float gl = __fmul_rn(g, dl);
-          float el, t1;
-          if (fp16sem) {
-            gl = __half2float(__float2half_rn(gl));
-            el = __half2float(__float2half_rn(__fadd_rn(ul, gl)));         // fp16 + fp16 (ed:918)
-            t1 = __half2float(__float2half_rn(__fmul_rn(sb, el)));         // 0-dim fp32 tensor * fp16 tensor -> fp16
-          } else {
-            el = __fadd_rn(ul, gl);
-            t1 = __fmul_rn(sb, el);
-          }
-          const float rx0 = __fdiv_rn(__fsub_rn(xl, t1), sa);               // ed:920-921
           // -d/dx0 [ w * mse(ref_up, x0) ] = -( (2/N) * (x0 - ref) * w )   (mse_loss backward, ed:932-935)
           const float grad = __fmul_rn(__fmul_rn(rrg_norm, __fsub_rn(x0v[cc][e], rx0)), rrg_w);
           res[cc][e] = __fadd_rn(res[cc][e], -grad);                        // ed:1078
@@ -368,6 +423,7 @@ __global__ void __launch_bounds__(256, 2) wave_epilogue_staged_kernel(const __gr
   if (staged) finish(std::true_type{});
   else finish(std::false_type{});
   ED_EMU_COUNT(staged ? 0 : 1);
+  if (!active) return;
   if (n_re > 0) renoise_stream4x4(res, A.noise + base0, (long long)P.B * P.C * hw, hw, S, n_re);
 #pragma unroll
   for (int cc = 0; cc < 4; ++cc)

@@ -40,13 +40,13 @@ void __syncthreads() { g_barrier.wait(); }
 template <typename OT>
 static int run(const ed::EpiArgs& A, int so, int sms, int* info) {
   const ed_plan_t& P = A.P;
-  ed::StagedCfg cfg = ed::staged_config(P, A.R1, so, sms);
+  ed::StagedCfg cfg = ed::staged_config(P, A.R1, so, sms, info ? info[5] : 3);
   if (!cfg.ok) return ED_ERR_UNSUPPORTED;
   cfg.g.vec_views = (info && info[7]) ? 0 : 1;   // test hook: scalar view loads
   if (info && info[6] > 0) {   // test hook: provision boxes `info[6]` rows too small -> tiles must take the global path
     cfg.g.bh = cfg.g.bh - info[6] > 0 ? cfg.g.bh - info[6] : 1;
     cfg.g.stage_bytes = ((unsigned)(cfg.g.bw * cfg.g.bh * P.C * so) + 127u) & ~127u;
-    cfg.smem = (size_t)A.R1 * 2 * cfg.g.stage_bytes;
+    cfg.smem = (size_t)A.R1 * 2 * cfg.g.stage_bytes + (size_t)cfg.g.bw * cfg.g.bh * P.C * 4;
   }
   for (auto& c : ed_emu_counters) c = 0;
   if (info) {

@@ -61,7 +61,7 @@ GEOS = [(1, 128, 256, 128, (64, 128), 64),      # cfg3
         (1, 72, 100, 64, (36, 50), 32)]         # unaligned low-res offset inside the canvas (g_lp = 7): boxes at odd coordinates
 
 
-def run_case(emu, cfg, mode, dtype, R1, sms, shrink=0, scalar_views=0):
+def run_case(emu, cfg, mode, dtype, R1, sms, shrink=0, scalar_views=0, origin=3):
     B, H, W, nat, ds, window = cfg
     geo = geometry.build_geometry(B, 4, H, W, nat, ds, window, window, nat - window)
     plan, keep = host_plan(geo)
@@ -87,7 +87,7 @@ def run_case(emu, cfg, mode, dtype, R1, sms, shrink=0, scalar_views=0):
     owner = ws.owner_map(geo, R1, idx, "cpu").to(torch.uint8).contiguous().view(-1)
     y, x0 = torch.full_like(x, float("nan")), torch.full_like(x, float("nan"))
     info = (ctypes.c_int * 16)()
-    info[6], info[7] = shrink, scalar_views
+    info[5], info[6], info[7] = origin, shrink, scalar_views
     rc = emu.emu_wave_epilogue(ctypes.byref(plan), ctypes.byref(sp), R1, x.data_ptr(), out.data_ptr(), native.dtype_code(dtype),
                                idx.data_ptr(), owner.data_ptr(), noise.data_ptr(), y.data_ptr(), x0.data_ptr(), sms, info)
     assert rc == 0, rc
@@ -105,10 +105,18 @@ def test_staged_epilogue_source_matches_spec_on_host(emu, cfg, mode, dtype):
     run_case(emu, cfg, mode, dtype, R1, sms=148)
 
 
+@pytest.mark.parametrize("origin", [0, 1, 2])
+def test_staged_epilogue_box_origin_policies(emu, origin):
+    """0: box at the first needed cell (unaligned, may hang over the canvas edge: zero fill), 1: 16-byte aligned start,
+    2: shifted back inside the canvas; the default 3 = both runs everywhere else."""
+    for cfg in (GEOS[3], GEOS[5], GEOS[7], GEOS[10]):
+        run_case(emu, cfg, "rrg", torch.bfloat16, 1 if cfg[0] == 2 else 3, sms=148, origin=origin)
+
+
 def test_staged_epilogue_large_cta_geometry_and_many_iterations(emu):
     # sms = 1: "fills the GPU twice" holds at once -> the 256-thread CTA (8 x 128 tile) is chosen
     info = run_case(emu, GEOS[0], "rrg", torch.bfloat16, 8, sms=1)
-    assert info[:4] == [32, 8, 64, 4] and info[4] == 16 * 2048
+    assert info[:4] == [32, 8, 64, 4] and info[4] == 16 * 2048 + 64 * 4 * 4 * 4
     # R1 = 21 (the signature default resampling_steps = 20) in fp32: boxes only fit with a smaller tile
     info = run_case(emu, GEOS[1], "rrg", torch.float32, 21, sms=1)
     assert info[4] <= 200 * 1024
