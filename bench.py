@@ -174,8 +174,8 @@ def kernel_rooflines(device, B=96, out_dtype=torch.bfloat16, iters=10, warm=3, o
     out = torch.randn(n, C, nat, nat, device=device, dtype=torch.float32).to(out_dtype)
     out_w2 = out[:2 * B + geo.nv * B]
     noise = torch.randn(n_re, B, C, H, W, device=device)
-    d_prm = torch.empty(3, ctypes.sizeof(native.StepParams), dtype=torch.uint8, device=device)
-    for slot, (flags, r1) in enumerate([(1, R1), (2, R1), (2, 1)]):
+    d_prm = torch.empty(4, ctypes.sizeof(native.StepParams), dtype=torch.uint8, device=device)
+    for slot, (flags, r1) in enumerate([(1, R1), (2, R1), (2, 1), (0, 1)]):
         sp = native.StepParams(guidance=10.0, sqrt_beta_t=0.96, sqrt_alpha_t=0.27, sqrt_alpha_prev=0.33, sqrt_dir=0.94,
                                rrg_weight=700.0, rrg_norm=2.0 / (C * H * W), flags=flags, n_renoise=n_re, R1=r1)
         for k in range(n_re):
@@ -199,6 +199,9 @@ def kernel_rooflines(device, B=96, out_dtype=torch.bfloat16, iters=10, warm=3, o
         # wave 2 of a repaint step while RRG is active (cfg3: one iteration) - the RRG launch of the BASELINE config
         "ed_wave_epilogue+rrg(wave2:R1=1)": (epi(2, 1, out_w2, idx_w2, owner_w2, None),
                                              Lb + win * so + glob(1, idx_w2, owner_w2, True) + H * W + cells + Lb),
+        # wave 2 of a repaint step after RRG has stopped (33 of the 50 steps at cfg3)
+        "ed_wave_epilogue(wave2:R1=1)": (epi(3, 1, out_w2, idx_w2, owner_w2, None),
+                                         Lb + win * so + glob(1, idx_w2, owner_w2, False) + H * W + Lb),
         # repaint_sampling=False: RRG in the R1 = 8 wave
         "ed_wave_epilogue+rrg": (epi(1, R1, out, idx, owner, None),
                                  Lb + win * so + glob(R1, idx, owner, True) + H * W + cells + Lb),

@@ -372,9 +372,32 @@ using namespace ed;
 
 // Tile-staged kernel (epilogue_staged.cuh).  ED_ERR_UNSUPPORTED: shape / alignment outside what it handles - the caller
 // then runs the direct kernel.
+template <typename OT, bool RENOISE, int CPT>
+static int launch_staged_as(const EpiArgs& A, int out_dtype, int sms, int origin, cudaStream_t stream) {
+  const ed_plan_t& P = A.P;
+  StagedCfg cfg = staged_config(P, A.R1, (int)sizeof(OT), sms, origin, CPT);
+  if (!cfg.ok) return ED_ERR_UNSUPPORTED;
+  const long long n_samples = 2LL * P.B * A.R1 + (long long)P.nv * P.B;
+  CUtensorMap tm;
+  // all samples of the wave as (dW, dH, samples * C) planes; box = cells x rows x CPT channels of one sample
+  int rc = encode_tmap_3d(&tm, A.unet_out, out_dtype, (uint64_t)P.dW, (uint64_t)P.dH, (uint64_t)n_samples * P.C,
+                          (uint32_t)cfg.g.bw, (uint32_t)cfg.g.bh, (uint32_t)CPT);
+  if (rc != ED_OK) return rc;
+  cfg.g.vec_views = 1;   // encode_tmap_3d checked the 16-byte alignment of unet_out; dH*dW*sizeof(OT) is a multiple of 16
+  static bool attr_set = false;   // one flag per template instantiation
+  if (!attr_set) {
+    ED_CUDA_CHECK(cudaFuncSetAttribute(wave_epilogue_staged_kernel<OT, RENOISE, CPT>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  const dim3 block(cfg.g.bx, cfg.g.by), grid(cfg.grid_x, cfg.grid_y, cfg.grid_z);
+  wave_epilogue_staged_kernel<OT, RENOISE, CPT><<<grid, block, cfg.smem, stream>>>(tm, A, cfg.g);
+  ED_LAUNCH_CHECK();
+  return ED_OK;
+}
+
 template <typename OT>
 static int launch_staged(const EpiArgs& A, int out_dtype, cudaStream_t stream) {
-  const ed_plan_t& P = A.P;
   static int sms = 0;
   if (!sms) {
     int dev = 0;
@@ -382,26 +405,14 @@ static int launch_staged(const EpiArgs& A, int out_dtype, cudaStream_t stream) {
     ED_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
   static const int origin = getenv("ED_STAGED_ORIGIN") ? atoi(getenv("ED_STAGED_ORIGIN")) : (ED_BOX_ALIGN | ED_BOX_CLAMP);
-  StagedCfg cfg = staged_config(P, A.R1, (int)sizeof(OT), sms, origin);
-  if (!cfg.ok) return ED_ERR_UNSUPPORTED;
-  const long long n_samples = 2LL * P.B * A.R1 + (long long)P.nv * P.B;
-  CUtensorMap tm;
-  // all samples of the wave as (dW, dH, samples * C) planes; box = cells x rows x C channels of one sample
-  int rc = encode_tmap_3d(&tm, A.unet_out, out_dtype, (uint64_t)P.dW, (uint64_t)P.dH, (uint64_t)n_samples * P.C,
-                          (uint32_t)cfg.g.bw, (uint32_t)cfg.g.bh, (uint32_t)P.C);
-  if (rc != ED_OK) return rc;
-  cfg.g.vec_views = 1;   // encode_tmap_3d checked the 16-byte alignment of unet_out; dH*dW*sizeof(OT) is a multiple of 16
-  static bool attr_set = false;   // one flag per template instantiation
-  if (!attr_set) {
-    ED_CUDA_CHECK(cudaFuncSetAttribute(wave_epilogue_staged_kernel<OT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
-  const dim3 block(cfg.g.bx, cfg.g.by), grid(cfg.grid_x, cfg.grid_y, cfg.grid_z);
-  wave_epilogue_staged_kernel<OT><<<grid, block, cfg.smem, stream>>>(tm, A, cfg.g);
-  ED_LAUNCH_CHECK();
-  return ED_OK;
+  static const int cpt_plain = getenv("ED_STAGED_CPT") ? atoi(getenv("ED_STAGED_CPT")) : 2;
+  // with a noise buffer: the re-noise stream keeps the launch DRAM-bound, 4 channels per thread amortise the per-pixel
+  // work best.  Without one (wave 2, no-repaint steps) the re-noise flag could not be honoured anyway: the lighter
+  // instantiation, channel pairs spread over the grid for twice the resident warps
+  if (A.noise) return launch_staged_as<OT, true, 4>(A, out_dtype, sms, origin, stream);
+  if (cpt_plain == 4) return launch_staged_as<OT, false, 4>(A, out_dtype, sms, origin, stream);
+  return launch_staged_as<OT, false, 2>(A, out_dtype, sms, origin, stream);
 }
-
 
 extern "C" {
 
@@ -438,7 +449,11 @@ static int launch_epilogue(const ed_plan_t* plan, const ed_step_params_t* d_para
   const int mode = g_epilogue_mode.load();
   if (mode != ED_EPILOGUE_DIRECT) {
     int rc = ED_ERR_UNSUPPORTED;
-    if (!peers && vec && (reinterpret_cast<uintptr_t>(owner) & 3) == 0) {
+    // AUTO: the staged kernel is the throughput shape (a thread carries 4 pixels x 4 channels behind a TMA wait); small
+    // launches - one or a few latents, everything L2-resident, latency-bound - keep the direct kernel, whose channels are
+    // spread over more and shorter threads (measured in the cfg3 pipeline at B = 1: 10 us vs 17 us per launch)
+    const bool big = (long long)(P.W / 4) * P.H * P.B >= 2LL * 148 * 256;
+    if (!peers && vec && (big || mode == ED_EPILOGUE_STAGED) && (reinterpret_cast<uintptr_t>(owner) & 3) == 0) {
       switch (out_dtype) {
         case ED_F32: rc = launch_staged<float>(A, out_dtype, stream); break;
         case ED_F16: rc = launch_staged<__half>(A, out_dtype, stream); break;

@@ -23,6 +23,13 @@
 #define ED_EMU_COUNT(i)   // host emulation only: path-coverage counters
 #endif
 
+#ifndef ED_STAGED_MINB
+#define ED_STAGED_MINB 2   // CTAs of 256 threads per SM the staged kernel is compiled for (register cap 65536 / (256 * MINB))
+#endif
+#ifndef ED_STAGED_MINB_PLAIN
+#define ED_STAGED_MINB_PLAIN 3
+#endif
+
 namespace ed {
 
 struct EpiArgs {
@@ -80,9 +87,10 @@ static inline int nearest_span_max(int n_out, int n_in, int tile, int offset = 0
 // so = bytes per UNet output element.  Preference: the largest CTA whose boxes fit twice per SM (<= 100 KB) and whose grid
 // fills the GPU at least twice; otherwise the smallest CTA that fits (more CTAs for small batches); otherwise one CTA
 // per SM (<= 200 KB); otherwise not applicable (the direct kernel runs).
-static inline StagedCfg staged_config(const ed_plan_t& P, int R1, int so, int sms, int origin = ED_BOX_ALIGN | ED_BOX_CLAMP) {
+static inline StagedCfg staged_config(const ed_plan_t& P, int R1, int so, int sms, int origin = ED_BOX_ALIGN | ED_BOX_CLAMP,
+                                      int cpt = 4) {
   StagedCfg best{};
-  if (P.C != 4 || (P.W & 3) || R1 <= 0 || P.B > 65535 || P.B <= 0) return best;
+  if (P.C != 4 || (P.W & 3) || R1 <= 0 || P.B * (P.C / cpt) > 65535 || P.B <= 0) return best;
   const int wv = P.W / 4;
   int bx = 32;
   while (bx > 1 && bx / 2 >= wv) bx /= 2;
@@ -95,11 +103,11 @@ static inline StagedCfg staged_config(const ed_plan_t& P, int R1, int so, int sm
     bw = (bw + align - 1) / align * align;
     const int bh = nearest_span_max(P.H, P.lh, by);
     if (bw > 256 || bh > 256) continue;
-    const unsigned stage = ((unsigned)(bw * bh * P.C * so) + 127u) & ~127u;
-    const size_t smem = (size_t)R1 * 2 * stage + (size_t)bw * bh * P.C * 4;   // boxes + the RRG low-res reference
+    const unsigned stage = ((unsigned)(bw * bh * cpt * so) + 127u) & ~127u;
+    const size_t smem = (size_t)R1 * 2 * stage + (size_t)bw * bh * cpt * 4;   // boxes + the RRG low-res reference
     if (smem > 200 * 1024) continue;
     const int gx = (P.W + bx * 4 - 1) / (bx * 4), gy = (P.H + by - 1) / by;
-    const long long ctas = (long long)gx * gy * P.B;
+    const long long ctas = (long long)gx * gy * P.B * (P.C / cpt);
     const int rank = smem <= 100 * 1024 ? (ctas >= 2LL * sms ? 3 : 2) : 1;
     // rank 3 stops the search (largest CTA wins); among rank <= 2 the later (smaller) CTA wins ties
     if (rank >= best_rank) {
@@ -108,7 +116,7 @@ static inline StagedCfg staged_config(const ed_plan_t& P, int R1, int so, int sm
       best.smem = smem;
       best.grid_x = gx;
       best.grid_y = gy;
-      best.grid_z = P.B;
+      best.grid_z = P.B * (P.C / cpt);
       best_rank = rank;
       if (rank == 3) break;
     }
@@ -136,23 +144,24 @@ ED_DEVICE void ld4_ro(const __nv_bfloat16* p, float out[4]) {
   for (int e = 0; e < 4; ++e) out[e] = __bfloat162float(h[e]);
 }
 
-// ed:692-704: x <- a_k x + b_k eps_k, sequential in k like the reference.  4 channels x 4 pixels per thread; the noise is
-// streamed once (evict-first), KB = 4 steps x 4 channels = 16 float4 loads in flight before the dependent chain.
-ED_DEVICE void renoise_stream4x4(float res[4][4], const float* nz, long long numel, long long hw,
-                                 const ed_step_params_t& S, int n_re) {
-  constexpr int KB = 4;
+// ed:692-704: x <- a_k x + b_k eps_k, sequential in k like the reference.  CPT channels x 4 pixels per thread; the noise
+// is streamed once (evict-first), KB steps x CPT channels = 16 float4 loads in flight before the dependent chain.
+template <int CPT>
+ED_DEVICE void renoise_stream(float res[CPT][4], const float* nz, long long numel, long long hw, const ed_step_params_t& S,
+                              int n_re) {
+  constexpr int KB = 16 / CPT;
   int k = 0;
   for (; k + KB <= n_re; k += KB) {
-    float4 t[4][KB];
+    float4 t[CPT][KB];
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc)
+    for (int cc = 0; cc < CPT; ++cc)
 #pragma unroll
       for (int j = 0; j < KB; ++j) t[cc][j] = __ldcs(reinterpret_cast<const float4*>(nz + (long long)(k + j) * numel + cc * hw));
 #pragma unroll
     for (int j = 0; j < KB; ++j) {
       const float a = S.renoise_a[k + j], bb = S.renoise_b[k + j];
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
+      for (int cc = 0; cc < CPT; ++cc) {
         res[cc][0] = __fadd_rn(__fmul_rn(a, res[cc][0]), __fmul_rn(bb, t[cc][j].x));
         res[cc][1] = __fadd_rn(__fmul_rn(a, res[cc][1]), __fmul_rn(bb, t[cc][j].y));
         res[cc][2] = __fadd_rn(__fmul_rn(a, res[cc][2]), __fmul_rn(bb, t[cc][j].z));
@@ -163,7 +172,7 @@ ED_DEVICE void renoise_stream4x4(float res[4][4], const float* nz, long long num
   for (; k < n_re; ++k) {
     const float a = S.renoise_a[k], bb = S.renoise_b[k];
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
+    for (int cc = 0; cc < CPT; ++cc) {
       const float4 t = __ldcs(reinterpret_cast<const float4*>(nz + (long long)k * numel + cc * hw));
       res[cc][0] = __fadd_rn(__fmul_rn(a, res[cc][0]), __fmul_rn(bb, t.x));
       res[cc][1] = __fadd_rn(__fmul_rn(a, res[cc][1]), __fmul_rn(bb, t.y));
@@ -173,17 +182,46 @@ ED_DEVICE void renoise_stream4x4(float res[4][4], const float* nz, long long num
   }
 }
 
-// grid: x over tiles of 4*bx columns, y over tiles of `by` rows, z = batch entry.  Thread = 4 consecutive pixels of one
-// row, all 4 latent channels.
-template <typename OT>
-__global__ void __launch_bounds__(256, 2) wave_epilogue_staged_kernel(const __grid_constant__ ED_TMAP tm, const EpiArgs A,
+// Correctly rounded a / b for ONE divisor shared by every element (b = sqrt(abar_t), uniform over the launch): the
+// reciprocal y = RN(1/b) is taken once, then two Markstein corrections q <- q + (a - b q) y with exact FMA remainders.  The
+// second correction starts from a faithful quotient, so its rounding is the IEEE quotient RN(a / b) (Markstein 1990;
+// tests/emu/div_check.c compares 10^9 random quotients, and every sqrt(abar_t) of the schedule, with the hardware
+// division bit for bit).  5 FMA-pipe instructions instead of __fdiv_rn's ~14 with its slow-path branch; inf / nan /
+// overflowing quotients take __fdiv_rn.
+struct DivBy {
+  float b, nb, y;
+};
+ED_DEVICE DivBy make_div_by(float b) {
+  DivBy d;
+  d.b = b;
+  d.nb = -b;
+  d.y = __frcp_rn(b);
+  return d;
+}
+ED_DEVICE float div_by(const DivBy& d, float a) {
+  float q = __fmul_rn(a, d.y);
+  float r = __fmaf_rn(d.nb, q, a);
+  q = __fmaf_rn(r, d.y, q);
+  r = __fmaf_rn(d.nb, q, a);
+  q = __fmaf_rn(r, d.y, q);
+  if (!(fabsf(q) <= 3.0e38f)) q = __fdiv_rn(a, d.b);
+  return q;
+}
+
+// RENOISE = false: instantiation without the re-noise stream (launches that pass no noise buffer: wave 2, no-repaint
+// steps); its register footprint is smaller (no 16 x float4 prefetch), so it is compiled for more resident CTAs.
+// CPT = channels per thread (4 or 2): CPT = 2 spreads the channel pairs over gridDim.z - half the registers and half the
+// shared memory per CTA, twice the resident warps; what a latency-bound launch (no noise stream to hide behind) needs.
+template <typename OT, bool RENOISE, int CPT>
+__global__ void __launch_bounds__(256, CPT == 2 ? 4 : (RENOISE ? ED_STAGED_MINB : ED_STAGED_MINB_PLAIN)) wave_epilogue_staged_kernel(const __grid_constant__ ED_TMAP tm, const EpiArgs A,
                                                                      const StagedGeom G) {
   ED_DYN_SMEM(smem_raw);
   __shared__ uint64_t bar;
   const ed_plan_t& P = A.P;
   const ed_step_params_t& S = *A.prm;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  const int b = blockIdx.z;
+  constexpr int CG = 4 / CPT;                       // channel groups, spread over gridDim.z with the batch
+  const int b = (int)blockIdx.z / CG, c_lo = ((int)blockIdx.z - b * CG) * CPT;
   const int R1 = A.R1;
   const int X0 = blockIdx.x * (G.bx * 4), Y0 = blockIdx.y * G.by;
   const int X1 = X0 + G.bx * 4 < P.W ? X0 + G.bx * 4 : P.W;
@@ -193,7 +231,7 @@ __global__ void __launch_bounds__(256, 2) wave_epilogue_staged_kernel(const __gr
   const int clo = __ldg(P.up_col + X0), chi = __ldg(P.up_col + X1 - 1);
   // box origin in canvas coordinates (the low-res latent sits at (g_tp, g_lp) inside a canvas plane, ed:405-406)
   int bx0 = P.g_lp + clo, by0 = P.g_tp + rlo;
-  if (G.origin & ED_BOX_ALIGN) bx0 = bx0 / G.col_align * G.col_align;
+  if (G.origin & ED_BOX_ALIGN) bx0 &= ~(G.col_align - 1);   // col_align = 16 / sizeof(OT): a power of two
   if (G.origin & ED_BOX_CLAMP) {
     if (bx0 + G.bw > P.dW && G.bw <= P.dW) bx0 = P.dW - G.bw;
     if (by0 + G.bh > P.dH && G.bh <= P.dH) by0 = P.dH - G.bh;
@@ -206,10 +244,10 @@ __global__ void __launch_bounds__(256, 2) wave_epilogue_staged_kernel(const __gr
   }
   __syncthreads();
   if (staged && tid == 0) {
-    const unsigned box_bytes = (unsigned)(G.bw * G.bh * P.C) * (unsigned)sizeof(OT);
+    const unsigned box_bytes = (unsigned)(G.bw * G.bh * CPT) * (unsigned)sizeof(OT);
     mbar_expect_tx(&bar, 2u * (unsigned)R1 * box_bytes);
     for (int ks = 0; ks < 2 * R1; ++ks)   // sample (k, s, b) = (2k + s) * B + b; planes of a sample are its C channels
-      tma_load_3d(smem_raw + (size_t)ks * G.stage_bytes, &tm, bx0, by0, (ks * P.B + b) * P.C, &bar);
+      tma_load_3d(smem_raw + (size_t)ks * G.stage_bytes, &tm, bx0, by0, (ks * P.B + b) * P.C + c_lo, &bar);
   }
   // threads beyond the latent's edge stay alive (the per-cell RRG phase below uses every thread and a CTA barrier): they
   // redo the work of the last valid position and skip the stores
@@ -223,7 +261,7 @@ __global__ void __launch_bounds__(256, 2) wave_epilogue_staged_kernel(const __gr
   const bool fp16sem = (flags & ED_FLAG_FP16_SEM) != 0;
   const bool rrg = (flags & ED_FLAG_RRG) != 0;
   const float g = S.guidance, sb = S.sqrt_beta_t, sa = S.sqrt_alpha_t, sap = S.sqrt_alpha_prev, sd = S.sqrt_dir;
-  const int n_re = (flags & ED_FLAG_RENOISE) ? S.n_renoise : 0;
+  const int n_re = (RENOISE && (flags & ED_FLAG_RENOISE)) ? S.n_renoise : 0;
   const int first_view_sample = 2 * P.B * R1;
   const long long hw = (long long)P.H * P.W;
   const long long plane = (long long)P.dH * P.dW;
@@ -238,10 +276,11 @@ __global__ void __launch_bounds__(256, 2) wave_epilogue_staged_kernel(const __gr
   const uchar4 ow = __ldg(reinterpret_cast<const uchar4*>(A.owner + pix));
   const int own[4] = {ow.x, ow.y, ow.z, ow.w};
   const int ur = __ldg(P.up_row + y);
-  const long long base0 = ((long long)b * P.C * P.H + y) * P.W + x;   // channel 0; + cc * hw per channel
-  float xin[4][4], uu[4][4];
+  const DivBy div_sa = make_div_by(sa);
+  const long long base0 = (((long long)b * P.C + c_lo) * P.H + y) * P.W + x;   // channel c_lo; + cc * hw per channel
+  float xin[CPT][4], uu[CPT][4];
 #pragma unroll
-  for (int cc = 0; cc < 4; ++cc) {
+  for (int cc = 0; cc < CPT; ++cc) {
     const float4 t = __ldg(reinterpret_cast<const float4*>(A.latent + base0 + cc * hw));
     xin[cc][0] = t.x; xin[cc][1] = t.y; xin[cc][2] = t.z; xin[cc][3] = t.w;
   }
@@ -250,14 +289,14 @@ __global__ void __launch_bounds__(256, 2) wave_epilogue_staged_kernel(const __gr
     ED_EMU_COUNT(4);
     const OT* vs = sample(first_view_sample + pr[0].y * P.B + b) + pr[0].z;
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) ld4_ro(vs + cc * plane, uu[cc]);
+    for (int cc = 0; cc < CPT; ++cc) ld4_ro(vs + (c_lo + cc) * plane, uu[cc]);
   } else {
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc)
+    for (int cc = 0; cc < CPT; ++cc)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int v_ = pr[e].y >= 0 ? pr[e].y : 0;   // several covering windows (view < 0): patched below
-        uu[cc][e] = ld_ro<OT>(sample(first_view_sample + v_ * P.B + b) + cc * plane + pr[e].z);
+        uu[cc][e] = ld_ro<OT>(sample(first_view_sample + v_ * P.B + b) + (c_lo + cc) * plane + pr[e].z);
       }
     ED_EMU_COUNT(one_view ? 5 : 6);
     if (!one_view) {   // rare: first-writer-wins walk over the covering windows where the value is non-zero (ed:852-861)
@@ -267,7 +306,7 @@ __global__ void __launch_bounds__(256, 2) wave_epilogue_staged_kernel(const __gr
           const int xe = x + e;
           const int r0 = __ldg(P.vrow_first + y), rn = __ldg(P.vrow_cnt + y);
           const int c0 = __ldg(P.vcol_first + xe), cn = __ldg(P.vcol_cnt + xe);
-          for (int cc = 0; cc < 4; ++cc) {
+          for (int cc = 0; cc < CPT; ++cc) {
             float u = 0.f;
             bool done = false;
             for (int a = 0; a < rn && !done; ++a)
@@ -276,7 +315,7 @@ __global__ void __launch_bounds__(256, 2) wave_epilogue_staged_kernel(const __gr
                 const int32_t* vt = P.views + v * 8;
                 const int yy = P.v_tp + __ldg(vt + 6) + (y - __ldg(vt + 0));
                 const int xx = P.v_lp + __ldg(vt + 7) + (xe - __ldg(vt + 2));
-                u = ld_ro<OT>(sample(first_view_sample + v * P.B + b) + cc * plane + (long long)yy * P.dW + xx);
+                u = ld_ro<OT>(sample(first_view_sample + v * P.B + b) + (c_lo + cc) * plane + (long long)yy * P.dW + xx);
                 done = (u != 0.f);
               }
             uu[cc][e] = u;
@@ -284,22 +323,10 @@ __global__ void __launch_bounds__(256, 2) wave_epilogue_staged_kernel(const __gr
         }
     }
   }
-  // RRG references (ed:886-940): the pixel the LAST iteration picked for the pixel's low-res cell, and owner + cell of the
-  // full-res pixel nearest-DOWNsampling reads for that cell (ed:688).  Per pixel only on unstaged tiles; staged tiles
-  // compute the low-res reference once per cell (phase B1)
-  int lat_off[4], kd[4], doff[4];
-  if (rrg && !staged) {
-    const int cells = P.lh * P.lw;
+  // what survives phase A per pixel: offset of its low-res cell inside a box plane (the pix_ref entries are dead from here)
+  int so[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int cell = pr[e].w;
-      const int pk = __ldg(A.idx + (long long)(R1 - 1) * cells + cell) & 3;
-      lat_off[e] = __ldg(P.cell_cand + cell * 4 + pk);
-      const int2 d = __ldg(reinterpret_cast<const int2*>(P.cell_down) + cell);
-      kd[e] = __ldg(A.owner + d.x);
-      doff[e] = d.y;
-    }
-  }
+  for (int e = 0; e < 4; ++e) so[e] = (ur - rb) * G.bw + (pr[e].w - ur * P.lw - cb);
 
   // ---- phase B: picks from the staged boxes (ST = true) or from global memory (ST = false: tile larger than the boxes) --
   if (staged) mbar_wait_bounded(&bar, 0);
@@ -324,7 +351,7 @@ __global__ void __launch_bounds__(256, 2) wave_epilogue_staged_kernel(const __gr
       el = __fadd_rn(ul, gl);
       t1 = __fmul_rn(sb, el);
     }
-    return __fdiv_rn(__fsub_rn(xl, t1), sa);                          // ed:920-921
+    return div_by(div_sa, __fsub_rn(xl, t1));                                 // ed:920-921
   };
 
   // ---- phase B1 (staged tiles with RRG): the low-res reference depends on the CELL, not on the pixel - one evaluation per
@@ -345,76 +372,95 @@ __global__ void __launch_bounds__(256, 2) wave_epilogue_staged_kernel(const __gr
       // inside the boxes at every exact ratio; general ratios may step outside at a tile border -> global load
       const bool in_box = (unsigned)(rd - rb) < (unsigned)G.bh && (unsigned)(cd - cb) < (unsigned)G.bw;
       ED_EMU_COUNT(in_box ? 2 : 3);
-      const int so = (r - rb) * G.bw + (c - cb), so2 = (rd - rb) * G.bw + (cd - cb);
+      const int sc = (r - rb) * G.bw + (c - cb), so2 = (rd - rb) * G.bw + (cd - cb);
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        const float xl = __ldg(A.latent + ((long long)b * P.C + cc) * hw + lo);                 // ed:910
-        const float ul = to_f32<OT>(sm[(size_t)(2 * (R1 - 1)) * stage_el + cc * plane_el + so]);
+      for (int cc = 0; cc < CPT; ++cc) {
+        const float xl = __ldg(A.latent + ((long long)b * P.C + c_lo + cc) * hw + lo);                 // ed:910
+        const float ul = to_f32<OT>(sm[(size_t)(2 * (R1 - 1)) * stage_el + cc * plane_el + sc]);
         float lun, lco;
         if (in_box) {
           lun = to_f32<OT>(sm[(size_t)(2 * kdn) * stage_el + cc * plane_el + so2]);
           lco = to_f32<OT>(sm[(size_t)(2 * kdn + 1) * stage_el + cc * plane_el + so2]);
         } else {
-          lun = ld_ro<OT>(sample((2 * kdn) * P.B + b) + cc * plane + d.y);
-          lco = ld_ro<OT>(sample((2 * kdn + 1) * P.B + b) + cc * plane + d.y);
+          lun = ld_ro<OT>(sample((2 * kdn) * P.B + b) + (c_lo + cc) * plane + d.y);
+          lco = ld_ro<OT>(sample((2 * kdn + 1) * P.B + b) + (c_lo + cc) * plane + d.y);
         }
-        rx0s[cc * plane_el + so] = low_res_x0(xl, ul, lun, lco);
+        rx0s[cc * plane_el + sc] = low_res_x0(xl, ul, lun, lco);
       }
     }
     __syncthreads();
   }
 
-  float res[4][4];
+  float res[CPT][4];
   auto finish = [&](auto staged_tag) {
     constexpr bool ST = decltype(staged_tag)::value;
-    // channel cc of wave sample (k, s, b) at the pixel's own low-res cell: shared-memory offset so / canvas offset go
-    auto own_cell = [&](int k, int s, int cc, int so, int go) -> float {
-      float v;
-      if constexpr (ST) v = to_f32<OT>(sm[(size_t)(2 * k + s) * stage_el + cc * plane_el + so]);
-      else v = ld_ro<OT>(sample((2 * k + s) * P.B + b) + cc * plane + go);
-      return v;
-    };
-    float x0v[4][4];
+    // ST: byte offset of (owner iteration, uncond, channel 0, own cell) inside the boxes; (s, cc) add uniform offsets.
+    // !ST: canvas-plane offset of the own cell (what pix_ref.x held)
+    const char* smb = reinterpret_cast<const char*>(smem_raw);
+    const int s_off = (int)G.stage_bytes, c_off = plane_el * (int)sizeof(OT);
+    int pb[4], go[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const int so = (ur - rb) * G.bw + (pr[e].w - ur * P.lw - cb);
+      pb[e] = 2 * own[e] * s_off + so[e] * (int)sizeof(OT);
+      go[e] = ST ? 0 : (P.g_tp + ur) * P.dW + P.g_lp + (so[e] - (ur - rb) * G.bw + cb);
+    }
+    auto own_cell = [&](int e, int k, int s, int cc) -> float {
+      float v;
+      if constexpr (ST) v = to_f32<OT>(*reinterpret_cast<const OT*>(smb + pb[e] + (2 * (k - own[e]) + s) * s_off + cc * c_off));
+      else v = ld_ro<OT>(sample((2 * k + s) * P.B + b) + (c_lo + cc) * plane + go[e]);
+      return v;
+    };
+    // unstaged tiles: per-pixel RRG references (ed:886-940): the pixel the LAST iteration picked for the pixel's low-res
+    // cell, and owner + canvas offset of the full-res pixel nearest-DOWNsampling reads for that cell (ed:688)
+    int lat_off[4], kd[4], doff[4];
+    if constexpr (!ST) {
+      if (rrg) {
+        const int cells = P.lh * P.lw;
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        const float un = own_cell(own[e], 0, cc, so, pr[e].x), co = own_cell(own[e], 1, cc, so, pr[e].x);
+        for (int e = 0; e < 4; ++e) {
+          const int cell = ur * P.lw + (so[e] - (ur - rb) * G.bw + cb);
+          const int pk = __ldg(A.idx + (long long)(R1 - 1) * cells + cell) & 3;
+          lat_off[e] = __ldg(P.cell_cand + cell * 4 + pk);
+          const int2 d = __ldg(reinterpret_cast<const int2*>(P.cell_down) + cell);
+          kd[e] = __ldg(A.owner + d.x);
+          doff[e] = d.y;
+        }
+      }
+    }
+    const float rrg_norm = S.rrg_norm, rrg_w = S.rrg_weight;
+    // channel by channel (the x0 of only one channel is live at a time)
+#pragma unroll
+    for (int cc = 0; cc < CPT; ++cc) {
+      float x0v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float un = own_cell(e, own[e], 0, cc), co = own_cell(e, own[e], 1, cc);
         float d = __fsub_rn(co, un);                                       // ed:440
         if (fp16sem) d = __half2float(__float2half_rn(d));                 // fp16 tensor under CUDA autocast / ed:655
         float gd = __fmul_rn(g, d);
         if (fp16sem) gd = __half2float(__float2half_rn(gd));               // python float * fp16 tensor -> fp16
         const float eps = __fadd_rn(uu[cc][e], gd);                        // ed:1031
-        const float x0 = __fdiv_rn(__fsub_rn(xin[cc][e], __fmul_rn(sb, eps)), sa);   // DDIM "predicted x_0"
-        x0v[cc][e] = x0;
-        res[cc][e] = __fadd_rn(__fmul_rn(sap, x0), __fmul_rn(sd, eps));              // x_{t-1}, eta = 0
+        const float x0 = div_by(div_sa, __fsub_rn(xin[cc][e], __fmul_rn(sb, eps)));   // DDIM "predicted x_0"
+        x0v[e] = x0;
+        res[cc][e] = __fadd_rn(__fmul_rn(sap, x0), __fmul_rn(sd, eps));    // x_{t-1}, eta = 0
       }
-    }
-    if (A.out_x0 && active) {
+      if (A.out_x0 && active)
+        *reinterpret_cast<float4*>(A.out_x0 + base0 + cc * hw) = make_float4(x0v[0], x0v[1], x0v[2], x0v[3]);
+      if (rrg) {
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc)
-        *reinterpret_cast<float4*>(A.out_x0 + base0 + cc * hw) = make_float4(x0v[cc][0], x0v[cc][1], x0v[cc][2], x0v[cc][3]);
-    }
-    if (rrg) {
-      const float rrg_norm = S.rrg_norm, rrg_w = S.rrg_weight;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int so = (ur - rb) * G.bw + (pr[e].w - ur * P.lw - cb);
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
+        for (int e = 0; e < 4; ++e) {
           float rx0;
           if constexpr (ST) {
-            rx0 = rx0s[cc * plane_el + so];
+            rx0 = rx0s[cc * plane_el + so[e]];
           } else {
-            const float xl = __ldg(A.latent + ((long long)b * P.C + cc) * hw + lat_off[e]);
-            const float ul = own_cell(R1 - 1, 0, cc, so, pr[e].x);
-            const float lun = ld_ro<OT>(sample((2 * kd[e]) * P.B + b) + cc * plane + doff[e]);
-            const float lco = ld_ro<OT>(sample((2 * kd[e] + 1) * P.B + b) + cc * plane + doff[e]);
+            const float xl = __ldg(A.latent + ((long long)b * P.C + c_lo + cc) * hw + lat_off[e]);
+            const float ul = own_cell(e, R1 - 1, 0, cc);
+            const float lun = ld_ro<OT>(sample((2 * kd[e]) * P.B + b) + (c_lo + cc) * plane + doff[e]);
+            const float lco = ld_ro<OT>(sample((2 * kd[e] + 1) * P.B + b) + (c_lo + cc) * plane + doff[e]);
             rx0 = low_res_x0(xl, ul, lun, lco);
           }
           // -d/dx0 [ w * mse(ref_up, x0) ] = -( (2/N) * (x0 - ref) * w )   (mse_loss backward, ed:932-935)
-          const float grad = __fmul_rn(__fmul_rn(rrg_norm, __fsub_rn(x0v[cc][e], rx0)), rrg_w);
+          const float grad = __fmul_rn(__fmul_rn(rrg_norm, __fsub_rn(x0v[e], rx0)), rrg_w);
           res[cc][e] = __fadd_rn(res[cc][e], -grad);                        // ed:1078
         }
       }
@@ -424,9 +470,10 @@ __global__ void __launch_bounds__(256, 2) wave_epilogue_staged_kernel(const __gr
   else finish(std::false_type{});
   ED_EMU_COUNT(staged ? 0 : 1);
   if (!active) return;
-  if (n_re > 0) renoise_stream4x4(res, A.noise + base0, (long long)P.B * P.C * hw, hw, S, n_re);
+  if constexpr (RENOISE)
+    if (n_re > 0) renoise_stream<CPT>(res, A.noise + base0, (long long)P.B * P.C * hw, hw, S, n_re);
 #pragma unroll
-  for (int cc = 0; cc < 4; ++cc)
+  for (int cc = 0; cc < CPT; ++cc)
     *reinterpret_cast<float4*>(A.out_latent + base0 + cc * hw) = make_float4(res[cc][0], res[cc][1], res[cc][2], res[cc][3]);
 }
 

@@ -4,13 +4,13 @@
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
 STAGES=${@:-"kernels roofline ncu e2e bench"}
-CASES='ed_wave_epilogue+renoise,ed_wave_epilogue+rrg(wave2:R1=1),ed_wave_epilogue+rrg'
+CASES='ed_wave_epilogue+renoise,ed_wave_epilogue+rrg(wave2:R1=1),ed_wave_epilogue(wave2:R1=1),ed_wave_epilogue+rrg'
 for s in $STAGES; do
   t0=$(date +%s)
   case $s in
     kernels) timeout 420 python -m pytest tests/test_gpu_kernels.py -x -q > gpurun_out/t_kernels.log 2>&1; rc=$? ;;
     roofline) timeout 240 python bench.py --roofline-only > gpurun_out/roofline.json 2> gpurun_out/roofline.err; rc=$? ;;
-    ncu) timeout 300 ncu --set full --clock-control none --import-source on -k regex:wave_epilogue_staged -c 3 -f \
+    ncu) timeout 300 ncu --set full --clock-control none --import-source on -k regex:wave_epilogue_staged -c 4 -f \
            -o gpurun_out/r1_epi_staged python bench.py --roofline-only --roofline-iters 1 --roofline-warm 0 \
            --roofline-cases "$CASES" > gpurun_out/ncu.log 2>&1; rc=$? ;;
     e2e) timeout 480 python -m pytest tests/test_gpu_e2e.py -x -q > gpurun_out/t_e2e.log 2>&1; rc=$? ;;

@@ -37,16 +37,16 @@ Barrier g_barrier;
 
 void __syncthreads() { g_barrier.wait(); }
 
-template <typename OT>
-static int run(const ed::EpiArgs& A, int so, int sms, int* info) {
+template <typename OT, bool RENOISE, int CPT>
+static int run_as(const ed::EpiArgs& A, int so, int sms, int* info) {
   const ed_plan_t& P = A.P;
-  ed::StagedCfg cfg = ed::staged_config(P, A.R1, so, sms, info ? info[5] : 3);
+  ed::StagedCfg cfg = ed::staged_config(P, A.R1, so, sms, info ? info[5] : 3, CPT);
   if (!cfg.ok) return ED_ERR_UNSUPPORTED;
   cfg.g.vec_views = (info && info[7]) ? 0 : 1;   // test hook: scalar view loads
   if (info && info[6] > 0) {   // test hook: provision boxes `info[6]` rows too small -> tiles must take the global path
     cfg.g.bh = cfg.g.bh - info[6] > 0 ? cfg.g.bh - info[6] : 1;
-    cfg.g.stage_bytes = ((unsigned)(cfg.g.bw * cfg.g.bh * P.C * so) + 127u) & ~127u;
-    cfg.smem = (size_t)A.R1 * 2 * cfg.g.stage_bytes + (size_t)cfg.g.bw * cfg.g.bh * P.C * 4;
+    cfg.g.stage_bytes = ((unsigned)(cfg.g.bw * cfg.g.bh * CPT * so) + 127u) & ~127u;
+    cfg.smem = (size_t)A.R1 * 2 * cfg.g.stage_bytes + (size_t)cfg.g.bw * cfg.g.bh * CPT * 4;
   }
   for (auto& c : ed_emu_counters) c = 0;
   if (info) {
@@ -54,7 +54,7 @@ static int run(const ed::EpiArgs& A, int so, int sms, int* info) {
     info[4] = (int)cfg.smem; info[5] = cfg.grid_x * cfg.grid_y * cfg.grid_z;
   }
   const long long n_samples = 2LL * P.B * A.R1 + (long long)P.nv * P.B;
-  ed::EmuTensorMap tm{static_cast<const uint8_t*>(A.unet_out), P.dW, P.dH, n_samples * P.C, cfg.g.bw, cfg.g.bh, P.C, so};
+  ed::EmuTensorMap tm{static_cast<const uint8_t*>(A.unet_out), P.dW, P.dH, n_samples * P.C, cfg.g.bw, cfg.g.bh, CPT, so};
   std::vector<uint8_t> smem(cfg.smem + 128);
   ed::emu_dyn_smem = smem.data();
   blockDim = dim3(cfg.g.bx, cfg.g.by, 1);
@@ -71,13 +71,21 @@ static int run(const ed::EpiArgs& A, int so, int sms, int* info) {
           th.emplace_back([&, t] {
             threadIdx = dim3(t % blockDim.x, t / blockDim.x, 0);
             blockIdx = dim3(bx, by, bz);
-            ed::wave_epilogue_staged_kernel<OT>(tm, A, cfg.g);
+            ed::wave_epilogue_staged_kernel<OT, RENOISE, CPT>(tm, A, cfg.g);
           });
         for (auto& x : th) x.join();
       }
   if (info)
     for (int i = 0; i < 7; ++i) info[8 + i] = (int)ed_emu_counters[i];
   return ED_OK;
+}
+
+// same dispatch as launch_staged() in csrc/epilogue.cu; info[9] (in) = channels per thread of the no-noise instantiation
+template <typename OT>
+static int run(const ed::EpiArgs& A, int so, int sms, int* info) {
+  if (A.noise) return run_as<OT, true, 4>(A, so, sms, info);
+  if (info && info[9] == 4) return run_as<OT, false, 4>(A, so, sms, info);
+  return run_as<OT, false, 2>(A, so, sms, info);
 }
 
 extern "C" int emu_wave_epilogue(const ed_plan_t* plan, const ed_step_params_t* params, int R1, const float* latent,

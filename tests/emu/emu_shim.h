@@ -58,6 +58,8 @@ static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline float __frcp_rn(float a) { return 1.0f / a; }
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 void __syncthreads();
 
 // path-coverage counters: 0 staged threads, 1 unstaged threads, 2 RRG down-cell inside the boxes, 3 outside (global load),

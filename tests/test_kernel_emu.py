@@ -61,7 +61,7 @@ GEOS = [(1, 128, 256, 128, (64, 128), 64),      # cfg3
         (1, 72, 100, 64, (36, 50), 32)]         # unaligned low-res offset inside the canvas (g_lp = 7): boxes at odd coordinates
 
 
-def run_case(emu, cfg, mode, dtype, R1, sms, shrink=0, scalar_views=0, origin=3):
+def run_case(emu, cfg, mode, dtype, R1, sms, shrink=0, scalar_views=0, origin=3, cpt=2):
     B, H, W, nat, ds, window = cfg
     geo = geometry.build_geometry(B, 4, H, W, nat, ds, window, window, nat - window)
     plan, keep = host_plan(geo)
@@ -87,9 +87,11 @@ def run_case(emu, cfg, mode, dtype, R1, sms, shrink=0, scalar_views=0, origin=3)
     owner = ws.owner_map(geo, R1, idx, "cpu").to(torch.uint8).contiguous().view(-1)
     y, x0 = torch.full_like(x, float("nan")), torch.full_like(x, float("nan"))
     info = (ctypes.c_int * 16)()
-    info[5], info[6], info[7] = origin, shrink, scalar_views
+    info[5], info[6], info[7], info[9] = origin, shrink, scalar_views, cpt
+    # like the pipeline, only re-noise launches pass a noise buffer (it selects the kernel instantiation)
     rc = emu.emu_wave_epilogue(ctypes.byref(plan), ctypes.byref(sp), R1, x.data_ptr(), out.data_ptr(), native.dtype_code(dtype),
-                               idx.data_ptr(), owner.data_ptr(), noise.data_ptr(), y.data_ptr(), x0.data_ptr(), sms, info)
+                               idx.data_ptr(), owner.data_ptr(), noise.data_ptr() if mode == "renoise" else None, y.data_ptr(),
+                               x0.data_ptr(), sms, info)
     assert rc == 0, rc
     want, want_x0 = ws.spec_epilogue(geo, prm, x, out, idx, noise)
     assert torch.equal(x0, want_x0), f"x0 max diff {(x0 - want_x0).abs().max().item():.3e} geometry {list(info)}"
@@ -115,8 +117,10 @@ def test_staged_epilogue_box_origin_policies(emu, origin):
 
 def test_staged_epilogue_large_cta_geometry_and_many_iterations(emu):
     # sms = 1: "fills the GPU twice" holds at once -> the 256-thread CTA (8 x 128 tile) is chosen
-    info = run_case(emu, GEOS[0], "rrg", torch.bfloat16, 8, sms=1)
+    info = run_case(emu, GEOS[0], "rrg", torch.bfloat16, 8, sms=1, cpt=4)
     assert info[:4] == [32, 8, 64, 4] and info[4] == 16 * 2048 + 64 * 4 * 4 * 4
+    info = run_case(emu, GEOS[0], "rrg", torch.bfloat16, 8, sms=1, cpt=2)
+    assert info[:4] == [32, 8, 64, 4] and info[4] == 16 * 1024 + 64 * 4 * 2 * 4
     # R1 = 21 (the signature default resampling_steps = 20) in fp32: boxes only fit with a smaller tile
     info = run_case(emu, GEOS[1], "rrg", torch.float32, 21, sms=1)
     assert info[4] <= 200 * 1024
@@ -132,3 +136,14 @@ def test_staged_epilogue_path_coverage(emu):
         tot = [a + b for a, b in zip(tot, info[8:15])]
         print(cfg, kw, info[:6], info[8:15])
     assert all(t > 0 for t in tot), tot
+
+
+def test_reciprocal_division_equals_ieee_division(tmp_path):
+    """struct DivBy (csrc/epilogue_staged.cuh): q = a*y, two FMA corrections == a / b for every divisor the DDIM schedule
+    produces and random ones (tests/emu/div_check.c; 6e7 quotients here, 1.2e9 with the default argument)."""
+    exe = str(tmp_path / "div_check")
+    r = subprocess.run(["gcc", "-O2", "-mfma", "-ffp-contract=off", "-o", exe, os.path.join(EMU_DIR, "div_check.c"), "-lm"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe, "20000"], capture_output=True, text=True)
+    assert r.returncode == 0 and " 0 mismatches" in r.stdout, r.stdout
