@@ -88,7 +88,7 @@ static inline int nearest_span_max(int n_out, int n_in, int tile, int offset = 0
 // fills the GPU at least twice; otherwise the smallest CTA that fits (more CTAs for small batches); otherwise one CTA
 // per SM (<= 200 KB); otherwise not applicable (the direct kernel runs).
 static inline StagedCfg staged_config(const ed_plan_t& P, int R1, int so, int sms, int origin = ED_BOX_ALIGN | ED_BOX_CLAMP,
-                                      int cpt = 4) {
+                                      int cpt = 4, int max_threads = 256) {
   StagedCfg best{};
   if (P.C != 4 || (P.W & 3) || R1 <= 0 || P.B * (P.C / cpt) > 65535 || P.B <= 0) return best;
   const int wv = P.W / 4;
@@ -96,7 +96,7 @@ static inline StagedCfg staged_config(const ed_plan_t& P, int R1, int so, int sm
   while (bx > 1 && bx / 2 >= wv) bx /= 2;
   const int align = 16 / so;
   int best_rank = 0;   // 3: fits twice + fills GPU, 2: fits twice, 1: fits once
-  for (int threads = 256; threads >= 64; threads >>= 1) {
+  for (int threads = max_threads; threads >= 64; threads >>= 1) {
     const int by = threads / bx;
     if (by < 1) break;
     int bw = nearest_span_max(P.W, P.lw, bx * 4, P.g_lp, (origin & ED_BOX_ALIGN) ? align : 1);
