@@ -85,9 +85,12 @@ def main():
         n = sum(a[0] for a in agg.values())
         ours = {k: v for k, v in agg.items() if k.startswith("ed::") or "ed::" in k or "wave_epilogue" in k or "tma_box" in k
                 or "pick_gather" in k or "owner_map" in k or "gather_views" in k}
-        md = [f"# ncu launch list ({tag}) (`ncu --metrics gpu__time_duration.sum --clock-control none -c 6000`)", "",
+        md = [f"# ncu launch list ({tag}) (`ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 8000 --launch-count 5000`)", "",
               "Command: `BENCH_GRAPHS=0 python bench.py --steps 1 --warmup 3 --no-extras` (cfg3, 1 GPU, CUDA graphs off so that every",
-              "kernel is a separate launch).  Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.",
+              "kernel is a separate launch; the first ~6000 launches are the stand-in UNet's weight initialisation, hence the skip).",
+              "The capture was cut by the stage's time limit after the launches listed here (steady-state denoise steps: part of a",
+              "wave-1 UNet forward, a wave epilogue, the gathers of the next wave).  Per-launch times under ncu are cold-cache and",
+              "serialised: compare SHARES, not absolutes.",
               "", f"total captured: {n} launches, {tot / 1e6:.1f} ms", "", "## libelastic_b200 kernels", "",
               "| kernel | launches | total us | avg us | share of captured GPU time |", "|---|---|---|---|---|"]
         for k, (c, t) in sorted(ours.items(), key=lambda kv: -kv[1][1]):

@@ -84,12 +84,20 @@ struct EmuTensorMap {
   int b0, b1, b2, es;
 };
 
+// mbarrier emulation: bits 0..39 = pending transaction bytes of the current phase, bits 40..63 = number of completed
+// phases.  One thread arms and (through the synchronous box copies) completes a phase; the others wait on a parity.
 static inline std::atomic<uint64_t>& emu_bar(uint64_t* bar) { return *reinterpret_cast<std::atomic<uint64_t>*>(bar); }
-static inline void mbar_init(uint64_t* bar, uint32_t) { emu_bar(bar).store(1ull << 62); }   // not armed
+static const uint64_t EMU_PENDING_MASK = (1ull << 40) - 1;
+static inline void mbar_init(uint64_t* bar, uint32_t) { emu_bar(bar).store(0); }
 static inline void fence_mbar_init() {}
-static inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { emu_bar(bar).store(bytes); }
-static inline void mbar_wait_bounded(uint64_t* bar, uint32_t) {
-  while (emu_bar(bar).load() != 0) std::this_thread::yield();
+static inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { emu_bar(bar).fetch_add(bytes); }
+// true once the phase with parity `parity` has completed (= the barrier's current phase has the other parity)
+static inline void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+  while (((emu_bar(bar).load() >> 40) & 1u) == parity) std::this_thread::yield();
+}
+static inline void emu_complete_tx(uint64_t* bar, uint64_t bytes) {
+  const uint64_t left = (emu_bar(bar).fetch_sub(bytes) - bytes) & EMU_PENDING_MASK;
+  if (left == 0) emu_bar(bar).fetch_add(1ull << 40);   // phase flip
 }
 static inline void tma_load_3d(void* smem_dst, const EmuTensorMap* m, int c0, int c1, int c2, uint64_t* bar) {
   uint8_t* dst = static_cast<uint8_t*>(smem_dst);
@@ -101,7 +109,7 @@ static inline void tma_load_3d(void* smem_dst, const EmuTensorMap* m, int c0, in
         if (x < 0 || x >= m->d0 || y < 0 || y >= m->d1 || z < 0 || z >= m->d2) memset(d, 0, m->es);
         else memcpy(d, m->base + ((z * m->d1 + y) * m->d0 + x) * m->es, m->es);
       }
-  emu_bar(bar).fetch_sub((uint64_t)m->b0 * m->b1 * m->b2 * m->es);
+  emu_complete_tx(bar, (uint64_t)m->b0 * m->b1 * m->b2 * m->es);
 }
 
 }  // namespace ed
