@@ -135,9 +135,11 @@ def test_wave_epilogue_matches_spec(cfg, mode, dtype, epilogue_kernel, R1=None):
     owner = torch.full((geo.H * geo.W,), 255, dtype=torch.uint8, device=DEV)
     native.check(L.ed_owner_map(ctypes.byref(plan), R1, native.ptr(idx), native.ptr(owner), st))
     assert torch.equal(owner.view(geo.H, geo.W).long(), ws.owner_map(geo, R1, idx, DEV))
+    # like the pipeline, only re-noise launches pass a noise buffer: NULL selects the staged kernel's lighter instantiation
+    # (no noise stream, channel pairs spread over the grid), a buffer its 4-channels-per-thread one
     native.check(L.ed_wave_epilogue(ctypes.byref(plan), native.ptr(d_prm), R1, native.ptr(x), native.ptr(out),
-                                    native.dtype_code(dtype), native.ptr(idx), native.ptr(owner), native.ptr(noise),
-                                    native.ptr(y), native.ptr(x0), st))
+                                    native.dtype_code(dtype), native.ptr(idx), native.ptr(owner),
+                                    native.ptr(noise) if mode == "renoise" else None, native.ptr(y), native.ptr(x0), st))
     torch.cuda.synchronize()
     want, want_x0 = ws.spec_epilogue(geo, prm, x, out, idx, noise)
     assert torch.equal(x0, want_x0), f"x0 max diff {(x0 - want_x0).abs().max().item():.3e}"
