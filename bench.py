@@ -486,7 +486,9 @@ def main():
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    epi0 = P.native.epilogue_launch_counts()
     sec, launches, _ = timed_run(host_io=False)
+    epi1 = P.native.epilogue_launch_counts()
     clk = clocks.stop() if rank == 0 else None
     ktimes = ed.kernel_times_ms()
     value = K / sec
@@ -497,7 +499,10 @@ def main():
             "unet": {"calls": ed.last_run["unet_calls"], "samples": ed.last_run["unet_samples"],
                      "collectives": ed.last_run["collectives"], "p2p_exchanges": ed.last_run.get("peer_exchanges", 0),
                      "exchange": ed.exchange, "exchange_fallback": ed.last_run.get("exchange_fallback")},
-            "kernels_in_step": {k: {"launches": n, "avg_us": round(1e3 * ms / max(n, 1), 2)} for k, (n, ms) in ktimes.items()}}
+            "kernels_in_step": {k: {"launches": n, "avg_us": round(1e3 * ms / max(n, 1), 2)} for k, (n, ms) in ktimes.items()},
+            # which wave-epilogue kernel AUTO took during this run (warm-up included): one latent per launch is a small,
+            # L2-resident launch -> the direct kernel; the TMA tile-staged kernel serves launches that fill the GPU
+            "epilogue_kernels": {"direct": epi1[0] - epi0[0], "staged": epi1[1] - epi0[1]}}
     if not args.no_extras:
         sec2, _, d2h = timed_run(host_io=True)
         n_cells = (H // 16) * (Wd // 16)

@@ -24,6 +24,7 @@ namespace ed {
 // EpiArgs: epilogue_staged.cuh
 
 static std::atomic<int> g_epilogue_mode{ED_EPILOGUE_AUTO};
+static std::atomic<long long> g_launches_direct{0}, g_launches_staged{0};
 
 // Which resampling iteration wrote target_direction[y, x] last (ed:637: every iteration overwrites where its mask is
 // set; ed:643-644: what is still NaN after the last iteration takes the last iteration's value).  All idx bytes are
@@ -462,6 +463,7 @@ static int launch_epilogue(const ed_plan_t* plan, const ed_step_params_t* d_para
         default: return ED_ERR_INVALID;
       }
     }
+    if (rc == ED_OK) g_launches_staged.fetch_add(1);
     if (rc != ED_ERR_UNSUPPORTED) return rc;
     if (mode == ED_EPILOGUE_STAGED) return ED_ERR_UNSUPPORTED;   // forced: do not silently take the other kernel
   }
@@ -487,6 +489,7 @@ static int launch_epilogue(const ed_plan_t* plan, const ed_step_params_t* d_para
   }
 #undef ED_EPI
   ED_LAUNCH_CHECK();
+  g_launches_direct.fetch_add(1);
   return ED_OK;
 }
 
@@ -502,6 +505,12 @@ int ed_wave_epilogue_peer(const ed_plan_t* plan, const ed_step_params_t* d_param
                           const uint8_t* owner, const float* noise, float* out_latent, float* out_x0, void* stream_) {
   return launch_epilogue(plan, d_params, R1, latent, nullptr, d_peer_out, world, per, out_dtype, idx, owner, noise,
                          out_latent, out_x0, stream_);
+}
+
+int ed_epilogue_launch_counts(int64_t* direct, int64_t* staged) {
+  if (direct) *direct = g_launches_direct.load();
+  if (staged) *staged = g_launches_staged.load();
+  return ED_OK;
 }
 
 int ed_set_epilogue_mode(int mode) {

@@ -67,6 +67,7 @@ EXPORTS = {
     "ed_wave_epilogue_peer": (C.c_int, [C.POINTER(Plan), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                         C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ed_set_epilogue_mode": (C.c_int, [C.c_int]),
+    "ed_epilogue_launch_counts": (C.c_int, [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "ed_renoise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ed_gather_cond": (C.c_int, [C.POINTER(Plan), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_int, C.c_void_p]),
@@ -121,6 +122,13 @@ def check(status: int, what: str = "") -> None:
         l = lib()
         msg = l.ed_strerror(status).decode()
         raise NativeError(f"libelastic_b200 {what}: {msg} (status {status}, cuda error {l.ed_last_cuda_error()})")
+
+
+def epilogue_launch_counts():
+    """(direct, staged): how many wave-epilogue launches of this process took each kernel."""
+    d, s = C.c_int64(0), C.c_int64(0)
+    check(lib().ed_epilogue_launch_counts(C.byref(d), C.byref(s)), "ed_epilogue_launch_counts")
+    return d.value, s.value
 
 
 def ptr(t):

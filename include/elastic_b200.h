@@ -162,6 +162,9 @@ int ed_wave_epilogue(const ed_plan_t* plan, const ed_step_params_t* d_params, in
  * stages, STAGED returns ED_ERR_UNSUPPORTED instead of falling back. */
 typedef enum { ED_EPILOGUE_AUTO = 0, ED_EPILOGUE_DIRECT = 1, ED_EPILOGUE_STAGED = 2 } ed_epilogue_mode;
 int ed_set_epilogue_mode(int mode);
+/* Process-wide number of ed_wave_epilogue / ed_wave_epilogue_peer launches that took the direct and the staged kernel
+ * (diagnostics: which kernel AUTO chose; either pointer may be NULL). */
+int ed_epilogue_launch_counts(int64_t* direct, int64_t* staged);
 
 /* ---- C1: the same epilogue fused with the multi-GPU exchange ---------------------------------
  * With wave samples sharded over `world` ranks (rank r holds samples [r*per, (r+1)*per) of the wave layout in its own
