@@ -30,6 +30,24 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert L.ed_strerror(-2).decode().startswith("unsupported")
 
 
+def test_epilogue_entry_points_reject_null_arguments_without_a_gpu():
+    """argument marshalling of the ABI v3 signatures (R1 after d_params; peer variant: pointer table, world, per): invalid
+    arguments are refused on the host before any CUDA call, so this runs without a device."""
+    L = native.lib()
+    st = ctypes.c_void_p(0)
+    assert L.ed_wave_epilogue(None, None, 1, None, None, 0, None, None, None, None, None, st) == -1
+    assert L.ed_wave_epilogue_peer(None, None, 1, None, None, 2, 1, 0, None, None, None, None, None, st) == -1
+    plan = native.Plan(B=1, C=4, H=8, W=8)
+    dummy = (ctypes.c_uint8 * 64)()
+    p = ctypes.cast(dummy, ctypes.c_void_p)
+    # R1 out of range / world, per invalid
+    assert L.ed_wave_epilogue(ctypes.byref(plan), p, 0, p, p, 0, p, p, None, p, None, st) == -1
+    assert L.ed_wave_epilogue(ctypes.byref(plan), p, 256, p, p, 0, p, p, None, p, None, st) == -1
+    assert L.ed_wave_epilogue_peer(ctypes.byref(plan), p, 1, p, p, 0, 0, 0, p, p, None, p, None, st) == -1
+    assert L.ed_set_epilogue_mode(3) == -1 and L.ed_set_epilogue_mode(native.EPILOGUE_AUTO) == 0
+    assert native.epilogue_launch_counts() == (0, 0)
+
+
 def test_struct_layouts_match_header_sizes():
     # ed_plan_t: 18 int32 + 18 pointers ; ed_step_params_t: 7 float + 5 int32 + 2*ED_MAX_RENOISE float ; ed_tiles_t: 10 int32 + 5 ptr
     assert ctypes.sizeof(native.Plan) == 18 * 4 + 18 * 8
