@@ -40,3 +40,15 @@ def test_large_batch_takes_the_staged_epilogue_and_matches_the_oracle():
     assert s1 - s0 == 3 and d1 == d0, f"expected 3 staged epilogue launches (2 waves + 1), got staged {s1 - s0}, direct {d1 - d0}"
     mse = torch.mean((lat - ref) ** 2).item()
     assert mse < 1e-8, f"mse {mse:.3e} max {(lat - ref).abs().max().item():.3e}"
+
+
+def test_error_behaviour_of_the_cuda_path_matches_the_reference():
+    """ed:200-201: sizes that are not multiples of 8 -> TypeError (the reference raises a str), before any kernel runs;
+    a condition image without a ControlNet -> ValueError."""
+    ed = make_ed("2.1", 4, "cuda")
+    with pytest.raises(TypeError):
+        ed.generate_image("a", "b", height=515, width=512, num_inference_steps=1, resampling_steps=0, progress=lambda it: it)
+    with pytest.raises(ValueError):
+        ed.denoise("a", "b", height=512, width=512, num_inference_steps=1, resampling_steps=0, progress=lambda it: it,
+                   condition_image=torch.rand(1, 3, 512, 512))
+    assert ed.last_run["kernel_launches"] == 0

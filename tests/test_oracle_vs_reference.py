@@ -85,3 +85,47 @@ def test_end_to_end_live(sd, H, W, T, R, vb):
     rp.seed_all(5, "cpu")
     mine = rp.denoise(m, "a", "b", H, W, T, resampling_steps=R)
     assert torch.equal(mine, lat)
+
+
+def test_module_level_schedulers_and_timelog_match_reference():
+    """ed:33-109: the RRG weight schedules and the TimeIt accumulator callers import next to the class."""
+    import importlib
+    from oracle.ref_shim import load_reference_module
+    ref = load_reference_module()
+    mine = importlib.import_module("elastic_diffusion")
+    for steps, scale, factor in [(40, 10.0, 1000), (40, 3.0, 1000), (8, 1.0, 0.01)]:
+        a, b = ref.CosineScheduler(steps, scale, factor), mine.CosineScheduler(steps, scale, factor)
+        assert [a(t) for t in range(steps + 3)] == [b(t) for t in range(steps + 3)]
+    for cls in ("LinearScheduler", "ConstScheduler"):
+        a, b = getattr(ref, cls)(10, 1000, 0), getattr(mine, cls)(10, 1000, 0)
+        assert [a(t) for t in range(13)] == [b(t) for t in range(13)]
+    assert hasattr(mine, "timelog") and sorted(n for n in dir(ref.timelog) if not n.startswith("_")) == \
+        sorted(n for n in dir(mine.timelog) if not n.startswith("_"))
+
+    @mine.timelog.time_function
+    def f(x):
+        return x + 1
+    assert f(1) == 2 and "FUNCTION_f" in mine.timelog.total_time
+    with mine.timelog.time_block("blk"):
+        pass
+    assert "BLOCK_blk" in mine.timelog.total_time
+
+
+def test_error_behaviour_matches_reference_on_the_host_side():
+    """ed:200-201 raises a str (= TypeError) for sizes that are not multiples of 8; ed:239-242 ValueError for an XL UNet whose
+    added-embedding width disagrees with the text encoder's projection dim."""
+    o = _ref("XL1.0", 1)
+    unet, vae, txt, proj = components("XL1.0")
+    from conftest import PKG
+    ed = PKG.ElasticDiffusion.from_components("cpu", unet, vae, None, txt, sd_version="XL1.0", projection_dim=proj)
+    for obj in (o, ed):
+        with pytest.raises(TypeError):
+            obj.get_views(1001, 512)
+    assert ed.get_views(1080, 1920, 64, 64, 64) == o.get_views(1080, 1920, h_ws=64, w_ws=64, stride=64)
+    good = ed._get_add_time_ids((4096, 8192), (0, 0), (4096, 8192), dtype=torch.float32)
+    assert torch.equal(good, o._get_add_time_ids((4096, 8192), (0, 0), (4096, 8192), dtype=torch.float32))
+    bad = PKG.ElasticDiffusion.from_components("cpu", unet, vae, None, txt, sd_version="XL1.0", projection_dim=proj + 1)
+    with pytest.raises(ValueError, match="Model expects an added time embedding vector"):
+        bad._get_add_time_ids((4096, 8192), (0, 0), (4096, 8192), dtype=torch.float32)
+    assert ed.get_downsample_size(1024, 2048) == o.get_downsample_size(1024, 2048)
+    assert ed.get_downsample_size(1080, 1920) == o.get_downsample_size(1080, 1920)
