@@ -7,9 +7,11 @@
 // of every iteration's output is touched anyway, by a different lane each time.  Here a CTA owns a tile of
 // `by` rows x `4*bx` columns of the latent; the low-res cells that nearest-upsampling reads for that tile form a rectangle
 // (up_row / up_col are non-decreasing), and ONE elected thread pulls that rectangle of ALL 2(R+1) global-pass outputs
-// into shared memory with TMA box loads (cp.async.bulk.tensor.3d: box = cells x rows x C channels, out-of-range columns
-// zero-filled, no alignment cases).  While the boxes are in flight every thread issues its own coalesced loads (latent,
-// per-pixel references, view windows); after the mbarrier flips, the per-pixel picks are shared-memory reads.
+// into shared memory with TMA box loads (cp.async.bulk.tensor.3d: box = cells x rows x channels; the box starts at a
+// 16-byte aligned column - measured: UTMALDG faults on an unaligned start address - and is shifted back inside the canvas
+// plane).  While the boxes are in flight every thread issues its own coalesced loads (latent, per-pixel references, view
+// windows); after the mbarrier flips, the per-pixel picks are shared-memory reads.  With RRG the low-res reference x0 is
+// evaluated once per (cell, channel) of the rectangle and shared through shared memory.
 //
 // This header is compiled twice: by nvcc into libelastic_b200.so, and by g++ with tests/emu/emu_shim.h (ED_HOST_EMU) into
 // a host emulation that the CPU test-suite checks against oracle/wave_spec.py - test infrastructure only, never loaded by
