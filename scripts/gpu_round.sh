@@ -15,7 +15,7 @@ for s in $STAGES; do
            --roofline-cases "$CASES" > gpurun_out/ncu.log 2>&1; rc=$? ;;
     e2e) timeout 480 python -m pytest tests/test_gpu_e2e.py -x -q > gpurun_out/t_e2e.log 2>&1; rc=$? ;;
     bench) timeout 420 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench.err; rc=$? ;;
-    launches) BENCH_GRAPHS=0 timeout 420 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 8000 --launch-count 5000 --csv \
+    launches) BENCH_GRAPHS=0 BENCH_CUPROF=1 timeout 420 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 5000 --csv \
            --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-extras > gpurun_out/launches.log 2>&1; rc=$? ;;
     smoke) timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; rc=$? ;;
     *) echo "unknown stage $s"; rc=99 ;;
