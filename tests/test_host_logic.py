@@ -216,3 +216,24 @@ def test_controlnet_twin_signatures_match_reference():
                      "guidance_scale", "controlnet_conditioning_scale", "resampling_steps", "new_p", "rrg_stop_t",
                      "rrg_init_weight", "rrg_scherduler_cls", "cosine_scale", "repaint_sampling", "progress",
                      "tiled_decoder", "grid"]
+
+
+def test_bench_algorithmic_byte_accounting_of_the_epilogue():
+    """bench.needed_global_elements: distinct (iteration, cond/uncond, cell) elements of the global-pass outputs that the
+    epilogue's arithmetic needs per (batch entry, channel) - the figure behind `roofline.achieved`."""
+    import bench
+    from oracle import wave_spec as ws
+    geo = geometry.build_geometry(1, 4, 128, 256, 128, (64, 128), 64, 64, 64)
+    cells = geo.lh * geo.lw
+    one = torch.zeros(1, cells, dtype=torch.uint8)
+    own1 = ws.owner_map(geo, 1, one, "cpu").view(-1).to(torch.uint8)
+    assert bench.needed_global_elements(geo, 1, one, own1, False) == 2 * cells          # cond + uncond of every cell, once
+    assert bench.needed_global_elements(geo, 1, one, own1, True) == 2 * cells           # RRG re-reads the same elements
+    g = torch.Generator().manual_seed(0)
+    idx = torch.randint(0, 4, (8, cells), generator=g, dtype=torch.uint8)
+    idx[0] = 0
+    own = ws.owner_map(geo, 8, idx, "cpu").view(-1).to(torch.uint8)
+    n = bench.needed_global_elements(geo, 8, idx, own, False)
+    # at most 4 owners per 2x2 cell (one per pixel), at least 1: between 2 and 8 elements per cell; ~7.2 for uniform picks
+    assert 2 * cells < n <= 8 * cells and abs(n / cells - 7.2) < 0.2
+    assert bench.needed_global_elements(geo, 8, idx, own, True) >= n
