@@ -1,6 +1,7 @@
 // Library-level entry points of libelastic_b200 + host helpers shared by the kernels' launchers.
 #include <cudaTypedefs.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "common.cuh"
@@ -19,6 +20,20 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
       fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
   });
   return fn;
+}
+
+// SM count of the CURRENT device, cached per device ordinal (a process may drive several GPUs, from several threads).
+int current_sm_count(int* sms) {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  ED_CUDA_CHECK(cudaGetDevice(&dev));
+  int v = (dev >= 0 && dev < 64) ? cache[dev].load(std::memory_order_relaxed) : 0;
+  if (!v) {
+    ED_CUDA_CHECK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+    if (dev >= 0 && dev < 64) cache[dev].store(v, std::memory_order_relaxed);
+  }
+  *sms = v;
+  return ED_OK;
 }
 
 int encode_tmap_3d_f32(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0,

@@ -144,6 +144,9 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
+// ---- host: SM count of the current device (per-device cache) ------------------------------------------------------
+int current_sm_count(int* sms);
+
 // ---- host: tensor-map encode through the runtime's driver entry point (no -lcuda at link time) -----------------
 // 3-D fp32 tensor (d0 fastest).  Returns ED_OK / ED_ERR_UNSUPPORTED (alignment) / ED_ERR_CUDA.
 int encode_tmap_3d_f32(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0,

@@ -386,12 +386,9 @@ static int launch_staged_as(const EpiArgs& A, int out_dtype, int sms, int origin
                           (uint32_t)cfg.g.bw, (uint32_t)cfg.g.bh, (uint32_t)CPT);
   if (rc != ED_OK) return rc;
   cfg.g.vec_views = 1;   // encode_tmap_3d checked the 16-byte alignment of unet_out; dH*dW*sizeof(OT) is a multiple of 16
-  static bool attr_set = false;   // one flag per template instantiation
-  if (!attr_set) {
-    ED_CUDA_CHECK(cudaFuncSetAttribute(wave_epilogue_staged_kernel<OT, RENOISE, CPT>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  // per launch: the opt-in is per DEVICE (a process-wide "already set" flag breaks the second GPU of a process); cheap
+  ED_CUDA_CHECK(cudaFuncSetAttribute(wave_epilogue_staged_kernel<OT, RENOISE, CPT>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const dim3 block(cfg.g.bx, cfg.g.by), grid(cfg.grid_x, cfg.grid_y, cfg.grid_z);
   wave_epilogue_staged_kernel<OT, RENOISE, CPT><<<grid, block, cfg.smem, stream>>>(tm, A, cfg.g);
   ED_LAUNCH_CHECK();
@@ -400,12 +397,8 @@ static int launch_staged_as(const EpiArgs& A, int out_dtype, int sms, int origin
 
 template <typename OT>
 static int launch_staged(const EpiArgs& A, int out_dtype, cudaStream_t stream) {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    ED_CUDA_CHECK(cudaGetDevice(&dev));
-    ED_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int sms = 0;
+  if (int rc = current_sm_count(&sms)) return rc;
   static const int origin = getenv("ED_STAGED_ORIGIN") ? atoi(getenv("ED_STAGED_ORIGIN")) : (ED_BOX_ALIGN | ED_BOX_CLAMP);
   static const int cpt_plain = getenv("ED_STAGED_CPT") ? atoi(getenv("ED_STAGED_CPT")) : 2;
   // with a noise buffer: the re-noise stream keeps the launch DRAM-bound, 4 channels per thread amortise the per-pixel

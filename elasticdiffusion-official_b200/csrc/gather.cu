@@ -97,19 +97,12 @@ static int launch_tma_box_copy(const float* src, uint64_t sW, uint64_t sH, uint6
   if (rc != ED_OK) return rc;
   rc = encode_tmap_3d_f32(&md, dst, dW, dH, dP, cols, J.bh, 1);
   if (rc != ED_OK) return rc;
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    ED_CUDA_CHECK(cudaGetDevice(&dev));
-    ED_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int sms = 0;
+  if (int rc2 = current_sm_count(&sms)) return rc2;
   const uint32_t stage_bytes = ((uint32_t)J.bh * cols * 4u + 127u) & ~127u;
   const size_t smem = (size_t)stage_bytes * kStages;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ED_CUDA_CHECK(cudaFuncSetAttribute(tma_box_copy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * kStages + 1024));
-    attr_set = true;
-  }
+  // per launch: the opt-in is per DEVICE (a process-wide "already set" flag breaks the second GPU of a process); cheap
+  ED_CUDA_CHECK(cudaFuncSetAttribute(tma_box_copy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * kStages + 1024));
   int grid = J.n_jobs < 2 * sms ? J.n_jobs : 2 * sms;  // persistent: 2 CTAs (1 driving thread each) per SM
   tma_box_copy_kernel<<<grid, 32, smem, stream>>>(ms, md, J);
   ED_LAUNCH_CHECK();

@@ -266,9 +266,12 @@ class RngLedger:
         for k in range(resampling_steps + 1):
             if k > 0:
                 idx = self._draw_cells(exclude)
-                drop = self._drop_draw().numpy().copy()                            # ed:541
+                drop = self._drop_draw()                                           # ed:541
+                # thresholds applied to the TORCH tensor like the reference: an int64 tensor against a Python float
+                # compares in float32, and 100 * drop_p is not always representable (0.8 -> 19.999999999999996)
                 drop[drop <= thr] = 0                                              # ed:542
                 drop[drop >= thr] = 1                                              # ed:543 -> P(new) = 30/101 at new_p = 0.3
+                drop = drop.numpy()
                 prev = idx * drop + prev * (1 - drop)                              # ed:544
             exclude[rows, prev] = True                                             # ed:675
             out[k] = prev.astype(np.uint8)
@@ -677,8 +680,9 @@ class ElasticDiffusion(nn.Module):
         self._require_cuda()
         L = native.lib()
         sf = self.vae_scale_factor
-        if height % sf or width % sf:
-            raise TypeError(f"height {height} and Width {width} must be divisable by {sf}")   # ed:200-201 raises a str
+        # heights / widths that are not multiples of the VAE factor are floored like the reference does (ed:998 draws a
+        # (height // 8, width // 8) latent and get_views only ever sees latent * 8, ed:817,827); only get_views() itself
+        # raises on such sizes (ed:200-201)
         self.last_run = dict(kernel_launches=0, unet_calls=0, unet_samples=0, collectives=0, vae_encodes=0, steps=0)
         self._shard_dtype = None
         self._sym = None
@@ -847,13 +851,13 @@ class ElasticDiffusion(nn.Module):
                 p["renoise"] = renoise_scalars(self.scheduler, ts[i + 1])
             return p
 
-        steps = list(enumerate(progress(ts)))
-        if max_steps is not None:
-            steps = steps[:max_steps]
+        n_steps = len(ts) if max_steps is None else min(len(ts), max_steps)
         # NOTE on buffer reuse: `noise` and `idx1` are single device buffers; the draws / copies of step i+1 are
         # enqueued on the main stream AFTER the kernels of step i, so stream order protects them.
         nxt = None
-        for i, t in steps:
+        for i, t in enumerate(progress(ts)):       # lazily: the caller's progress bar advances once per finished step (ed:1013)
+            if i >= n_steps:
+                break
             p = nxt if nxt is not None else plan_step(i)
             nxt = None
             repaint, w, sc = p["repaint"], p["w"], p["sc"]
@@ -881,7 +885,7 @@ class ElasticDiffusion(nn.Module):
             else:
                 prm.flags = native.FLAG_RRG if rrg_on else 0
                 run_wave(x, t, idx1, R + 1, strips_g, strips_v, prm, 0, None, x_next, x0_buf, text1, pool1)
-            if i + 1 < len(ts) and (max_steps is None or i + 1 < max_steps):
+            if i + 1 < n_steps:
                 nxt = plan_step(i + 1)          # look-ahead: host RNG chain of the next step runs under this step's GPU work
             x, x_next = x_next, x                                                              # ed:1078
             self.last_run["steps"] += 1

@@ -7,7 +7,8 @@ synthetic UNet / VAE / scheduler.  Every line of the hot path that then executes
 
 /root/reference exists only in the build container: this file is used by `scripts/make_golden.py` (which writes
 the committed fixtures under tests/golden/) and by CPU tests that are skipped when the reference is absent.
-Nothing in `-m gpu` tests, smoke() or bench.py reads /root/reference at run time.
+Nothing in `-m gpu` tests, smoke() or bench.py reads /root/reference at run time; bench.py's reference legs load the
+same unmodified files from `baseline/_ref/` (installed by scripts/install_reference.py, git-ignored, shipped to the box).
 """
 from __future__ import annotations
 
@@ -20,7 +21,10 @@ from types import SimpleNamespace
 import torch
 import torch.nn as nn
 
-REF_CANDIDATES = [os.environ.get("ELASTIC_REFERENCE_DIR", ""), "/root/reference"]
+# /root/reference exists in the build container only; baseline/_ref is the pip-installed copy of the same unmodified files
+# (scripts/install_reference.py, git-ignored) that travels to the GPU box - bench.py's reference legs use it there.
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_CANDIDATES = [os.environ.get("ELASTIC_REFERENCE_DIR", ""), "/root/reference", os.path.join(_ROOT, "baseline", "_ref")]
 
 
 def reference_dir():

@@ -13,7 +13,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-syn = importlib.import_module("elasticdiffusion-official_b200.synthetic")
+import standins as syn  # noqa: E402
 from oracle.ddim_restated import DDIMRestated  # noqa: E402
 from oracle.ref_shim import build_reference, run_reference  # noqa: E402
 
@@ -26,6 +26,9 @@ CASES = {
                                                prompts=["a cat", "a dog on a bench"])),
     "sd21_640x896_T3_R2_norepaint": ("2.1", 2, dict(height=640, width=896, num_inference_steps=3, resampling_steps=2,
                                                     repaint_sampling=False, cosine_scale=3.0)),
+    # non-default new_p whose threshold 100 * (1 - new_p) = 19.999999999999996 is not representable (float32 compare, ed:542)
+    "sd21_512x1024_T3_R3_newp08": ("2.1", 8, dict(height=512, width=1024, num_inference_steps=3, resampling_steps=3,
+                                                  new_p=0.8)),
     "xl_1024x2048_T3_R7": ("XL1.0", 16, dict(height=1024, width=2048, num_inference_steps=3, resampling_steps=7)),
     "xl_2048x2048_T2_R2_tiled": ("XL1.0", 16, dict(height=2048, width=2048, num_inference_steps=2, resampling_steps=2,
                                                    tiled_decoder=True)),

@@ -7,7 +7,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-syn = importlib.import_module("elasticdiffusion-official_b200.synthetic")
+import standins as syn  # noqa: E402
 dev = torch.device("cuda")
 unet = syn.StandInUNet("XL1.0", device=dev, dtype=torch.bfloat16).eval()
 t = torch.tensor(981, device=dev)

@@ -10,6 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+import standins  # noqa: E402
+
 PKG = importlib.import_module("elasticdiffusion-official_b200")
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
@@ -54,7 +56,7 @@ def load_golden(name):
 
 def components(sd, device="cpu"):
     """Same synthetic modules as scripts/make_golden.py (fixed-seed weights)."""
-    syn = PKG.synthetic
+    import standins as syn
     xl = sd.startswith("XL")
     unet = syn.StubUNet(sample_size=128 if xl else 64, cross_dim=16, xl=xl, pooled_dim=8).to(device)
     vae = syn.StubVAE().to(device)
@@ -67,7 +69,7 @@ def make_ed(sd, vb, device="cpu", controlnet=False):
     if controlnet:
         return PKG.controlnet.ElasticDiffusion.from_components(
             device, unet, vae, None, txt, sd_version=sd, view_batch_size=vb, projection_dim=proj,
-            controlnet=PKG.synthetic.StubControlNet().to(device))
+            controlnet=standins.StubControlNet().to(device))
     return PKG.ElasticDiffusion.from_components(device, unet, vae, None, txt, sd_version=sd, view_batch_size=vb,
                                                 projection_dim=proj)
 
@@ -76,7 +78,7 @@ def oracle_models(sd, vb, device="cpu", controlnet=False):
     from oracle import reference_port as rp
     from oracle.ddim_restated import DDIMRestated
     unet, vae, txt, proj = components(sd, device)
-    cn = PKG.synthetic.StubControlNet().to(device) if controlnet else None
+    cn = standins.StubControlNet().to(device) if controlnet else None
     return rp.Models(unet, vae, DDIMRestated(), txt, sd, device, vb, projection_dim=proj, controlnet=cn)
 
 

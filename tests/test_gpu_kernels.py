@@ -102,6 +102,13 @@ def epilogue_kernel(request):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("epilogue_kernel", ["direct", "staged"], indirect=True)
 def test_wave_epilogue_matches_spec(cfg, mode, dtype, epilogue_kernel, R1=None):
+    _epilogue_case(cfg, mode, dtype, R1)
+
+
+def _epilogue_case(cfg, mode, dtype, R1=None, peer_world=None):
+    """One fused-epilogue launch against the contract emulation.  `peer_world`: go through ed_wave_epilogue_peer with the
+    wave's samples split over `peer_world` per-"rank" buffers (sample s lives in buffer s // per at index s % per) - the
+    multi-GPU entry point exercised on ONE GPU: the pointer table simply points at separate local allocations."""
     L = native.lib()
     geo = build(cfg)
     plan, keep = upload(geo)
@@ -137,13 +144,44 @@ def test_wave_epilogue_matches_spec(cfg, mode, dtype, epilogue_kernel, R1=None):
     assert torch.equal(owner.view(geo.H, geo.W).long(), ws.owner_map(geo, R1, idx, DEV))
     # like the pipeline, only re-noise launches pass a noise buffer: NULL selects the staged kernel's lighter instantiation
     # (no noise stream, channel pairs spread over the grid), a buffer its 4-channels-per-thread one
-    native.check(L.ed_wave_epilogue(ctypes.byref(plan), native.ptr(d_prm), R1, native.ptr(x), native.ptr(out),
-                                    native.dtype_code(dtype), native.ptr(idx), native.ptr(owner),
-                                    native.ptr(noise) if mode == "renoise" else None, native.ptr(y), native.ptr(x0), st))
+    if peer_world is None:
+        native.check(L.ed_wave_epilogue(ctypes.byref(plan), native.ptr(d_prm), R1, native.ptr(x), native.ptr(out),
+                                        native.dtype_code(dtype), native.ptr(idx), native.ptr(owner),
+                                        native.ptr(noise) if mode == "renoise" else None, native.ptr(y), native.ptr(x0), st))
+    else:
+        per = (n + peer_world - 1) // peer_world          # pipeline._unet's partition: ragged last rank, idle ranks
+        bufs = []
+        for r in range(peer_world):
+            buf = torch.full((per,) + tuple(out.shape[1:]), float("nan"), device=DEV, dtype=dtype)   # never-written slots
+            lo, hi = min(r * per, n), min((r + 1) * per, n)
+            buf[:hi - lo] = out[lo:hi]
+            bufs.append(buf)
+        ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=DEV)
+        native.check(L.ed_wave_epilogue_peer(ctypes.byref(plan), native.ptr(d_prm), R1, native.ptr(x), native.ptr(ptrs),
+                                             peer_world, per, native.dtype_code(dtype), native.ptr(idx), native.ptr(owner),
+                                             native.ptr(noise) if mode == "renoise" else None, native.ptr(y),
+                                             native.ptr(x0), st))
     torch.cuda.synchronize()
     want, want_x0 = ws.spec_epilogue(geo, prm, x, out, idx, noise)
     assert torch.equal(x0, want_x0), f"x0 max diff {(x0 - want_x0).abs().max().item():.3e}"
     assert torch.equal(y, want), f"latent max diff {(y - want).abs().max().item():.3e}"
+
+
+@pytest.mark.parametrize("cfg", [GEOS[0], GEOS[3], GEOS[4], GEOS[5], GEOS[8], GEOS[9]])
+@pytest.mark.parametrize("mode", ["plain", "renoise", "rrg"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_wave_epilogue_peer_matches_spec_on_one_gpu(cfg, mode, dtype, world):
+    """ed_wave_epilogue_peer (the PEER = true instantiation that the N-GPU pipeline launches) with world in {2, 3, 8}:
+    ragged `per`, idle ranks (world 8 with 12 samples -> ranks 6, 7 own nothing), bit-exact against the same spec."""
+    _epilogue_case(cfg, mode, dtype, R1=(1 if mode == "rrg" and cfg[0] == 2 else 4), peer_world=world)
+
+
+def test_wave_epilogue_peer_cfg3_partition():
+    """the exact partitions of the cfg3 bench at 8 GPUs: wave 1 = 20 samples (per 3, rank 7 idle beyond 2), wave 2 = 6."""
+    _epilogue_case(GEOS[0], "renoise", torch.bfloat16, R1=8, peer_world=8)
+    _epilogue_case(GEOS[0], "rrg", torch.bfloat16, R1=1, peer_world=8)
+    _epilogue_case(GEOS[0], "plain", torch.bfloat16, R1=1, peer_world=4)
 
 
 @pytest.mark.parametrize("cfg,R1,dtype", [(GEOS[0], 8, torch.bfloat16),      # cfg3 wave 1
@@ -154,7 +192,7 @@ def test_wave_epilogue_matches_spec(cfg, mode, dtype, epilogue_kernel, R1=None):
 @pytest.mark.parametrize("mode", ["renoise", "rrg"])
 @pytest.mark.parametrize("epilogue_kernel", ["staged"], indirect=True)
 def test_staged_epilogue_many_iterations_and_large_ctas(cfg, R1, dtype, mode, epilogue_kernel):
-    test_wave_epilogue_matches_spec(cfg, mode, dtype, epilogue_kernel, R1=R1)
+    _epilogue_case(cfg, mode, dtype, R1=R1)
 
 
 def test_auto_mode_takes_the_direct_kernel_where_staging_does_not_apply():

@@ -162,10 +162,17 @@ def test_ddim_scalars_match_oracle_step():
 
 
 # ---- RNG ledger vs oracle trace ---------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", ["sd21_512x1024_T4_R4", "sd15_512x512_T5_R3", "xl_1080x1920_T2_R2"])
-def test_ledger_replays_the_reference_pick_indices(name):
+@pytest.mark.parametrize("name,new_p", [("sd21_512x1024_T4_R4", None), ("sd15_512x512_T5_R3", None),
+                                        ("xl_1080x1920_T2_R2", None),
+                                        # 100 * (1 - new_p) is not representable for these: the keep/new threshold must
+                                        # compare like torch does (int64 tensor vs Python float -> float32), ed:541-543
+                                        ("sd21_512x1024_T4_R4", 0.8), ("sd21_512x1024_T4_R4", 0.9),
+                                        ("sd15_512x512_T5_R3", 0.34), ("sd15_512x512_T5_R3", 0.55)])
+def test_ledger_replays_the_reference_pick_indices(name, new_p):
     g = load_golden(name)
     kw = oracle_kwargs(g["kwargs"])
+    if new_p is not None:
+        kw["new_p"] = new_p
     m = oracle_models(g["sd_version"], g["view_batch_size"])
     rp.seed_all(g["seed"], "cpu")
     trace = {}
