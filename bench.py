@@ -154,11 +154,8 @@ def kernel_rooflines(device, B=96, out_dtype=torch.bfloat16, iters=10, warm=3, o
     L = native.lib()
     C, H, W, nat, R1, n_re = 4, 128, 256, 128, 8, 20
     geo = geometry.build_geometry(B, C, H, W, nat, (64, 128), 64, 64, 64)
-    keep = {k: torch.tensor(v if len(v) else [0], dtype=torch.int32, device=device) for k, v in geo.tables.items()}
+    plan, keep = native.plan_from_geometry(geo, device)
     lp, rp, tp, bp = geo.g_pad
-    plan = native.Plan(B=B, C=C, H=H, W=W, dH=nat, dW=nat, lh=geo.lh, lw=geo.lw, g_tp=tp, g_lp=lp, nv=geo.nv,
-                       nvr=geo.nvr, nvc=geo.nvc, vh=geo.vh, vw=geo.vw, v_tp=0, v_lp=0,
-                       **{k: v.data_ptr() for k, v in keep.items()})
     st = native.stream_handle()
     x = torch.randn(B, C, H, W, device=device)
     y = torch.empty_like(x)
@@ -260,13 +257,16 @@ def kernel_rooflines(device, B=96, out_dtype=torch.bfloat16, iters=10, warm=3, o
         if only and name not in only:
             continue
         res[name] = time_case(name, fn, nbytes)
-    if ab and not only:     # A/B: the direct (scattered-load) epilogue kernel on the same inputs
-        native.check(L.ed_set_epilogue_mode(native.EPILOGUE_DIRECT))
-        try:
-            for name, (fn, nbytes) in epi_cases.items():
-                res[name + "[direct kernel]"] = time_case(name, fn, nbytes)
-        finally:
-            native.check(L.ed_set_epilogue_mode(native.EPILOGUE_AUTO))
+    if ab and not only:     # A/B on the same inputs: the round-1 kernels (AUTO takes the half kernels for launches without a
+        for tag, mode in (("[staged kernel]", native.EPILOGUE_STAGED), ("[direct kernel]", native.EPILOGUE_DIRECT)):   # noise stream)
+            native.check(L.ed_set_epilogue_mode(mode))
+            try:
+                for name, (fn, nbytes) in epi_cases.items():
+                    if tag == "[staged kernel]" and name.endswith("+renoise"):
+                        continue                     # AUTO already ran the staged kernel for this one
+                    res[name + tag] = time_case(name, fn, nbytes)
+            finally:
+                native.check(L.ed_set_epilogue_mode(native.EPILOGUE_AUTO))
     return res, peak, how
 
 
@@ -646,9 +646,10 @@ def main():
                      "collectives": ed.last_run["collectives"], "p2p_exchanges": ed.last_run.get("peer_exchanges", 0),
                      "exchange": ed.exchange, "exchange_fallback": ed.last_run.get("exchange_fallback")},
             "kernels_in_step": {k: {"launches": n, "avg_us": round(1e3 * ms / max(n, 1), 2)} for k, (n, ms) in ktimes.items()},
-            # which wave-epilogue kernel AUTO took during this run (warm-up included): one latent per launch is a small,
-            # L2-resident launch -> the direct kernel; the TMA tile-staged kernel serves launches that fill the GPU
-            "epilogue_kernels": {"direct": epi1[0] - epi0[0], "staged": epi1[1] - epi0[1]}}
+            # which wave-epilogue kernel AUTO took during this run (warm-up included): launches without a noise stream ->
+            # the half kernels (exact 1/2 ratio); re-noise launches: one latent per launch is small and L2-resident -> the
+            # direct kernel, the TMA tile-staged kernel serves launches that fill the GPU
+            "epilogue_kernels": {"direct": epi1[0] - epi0[0], "staged": epi1[1] - epi0[1], "half": epi1[2] - epi0[2]}}
     if not args.no_extras:
         sec2, _, d2h = timed_run(host_io=True)
         n_cells = (H // 16) * (Wd // 16)

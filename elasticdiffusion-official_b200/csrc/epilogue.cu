@@ -13,6 +13,7 @@
 
 #include <atomic>
 
+#include "epilogue_half.cuh"
 #include "epilogue_staged.cuh"
 
 #ifndef ED_EPI_MINB
@@ -24,7 +25,7 @@ namespace ed {
 // EpiArgs: epilogue_staged.cuh
 
 static std::atomic<int> g_epilogue_mode{ED_EPILOGUE_AUTO};
-static std::atomic<long long> g_launches_direct{0}, g_launches_staged{0};
+static std::atomic<long long> g_launches_direct{0}, g_launches_staged{0}, g_launches_half{0};
 
 // Which resampling iteration wrote target_direction[y, x] last (ed:637: every iteration overwrites where its mask is
 // set; ed:643-644: what is still NaN after the last iteration takes the last iteration's value).  All idx bytes are
@@ -409,6 +410,36 @@ static int launch_staged(const EpiArgs& A, int out_dtype, cudaStream_t stream) {
   return launch_staged_as<OT, false, 2>(A, out_dtype, sms, origin, stream);
 }
 
+// Half kernels (epilogue_half.cuh): plan flag ED_PLAN_HALF_FAST, no noise stream.  ED_ERR_UNSUPPORTED: outside their domain.
+template <typename OT, bool MULTI>
+static int launch_half_as(const EpiArgs& A, const HalfCfg& cfg, cudaStream_t stream) {
+  const dim3 block(cfg.bx, cfg.by), grid(cfg.grid_x, cfg.grid_y, cfg.grid_z);
+  if (A.peers) {
+    if (cfg.smem > 48 * 1024)
+      ED_CUDA_CHECK(cudaFuncSetAttribute(wave_epilogue_half_kernel<OT, MULTI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    wave_epilogue_half_kernel<OT, MULTI, true><<<grid, block, cfg.smem, stream>>>(A);
+  } else {
+    if (cfg.smem > 48 * 1024)
+      ED_CUDA_CHECK(cudaFuncSetAttribute(wave_epilogue_half_kernel<OT, MULTI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    wave_epilogue_half_kernel<OT, MULTI, false><<<grid, block, cfg.smem, stream>>>(A);
+  }
+  ED_LAUNCH_CHECK();
+  return ED_OK;
+}
+
+template <typename OT>
+static int launch_half(const EpiArgs& A, cudaStream_t stream) {
+  const HalfCfg cfg = half_config(A.P, A.R1, (int)sizeof(OT));
+  if (!cfg.ok || A.noise) return ED_ERR_UNSUPPORTED;
+  auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  // peer buffers come from symmetric-memory allocations (>= 256-byte aligned); the local pointers are checked here
+  if (!aligned(A.latent) || !aligned(A.out_latent) || (A.out_x0 && !aligned(A.out_x0)) || (A.unet_out && !aligned(A.unet_out)) ||
+      (A.R1 > 1 && (reinterpret_cast<uintptr_t>(A.owner) & 7)) || (reinterpret_cast<uintptr_t>(A.idx) & 3) ||
+      (((long long)(A.R1 - 1) * A.P.lh * A.P.lw) & 3))
+    return ED_ERR_UNSUPPORTED;
+  return A.R1 > 1 ? launch_half_as<OT, true>(A, cfg, stream) : launch_half_as<OT, false>(A, cfg, stream);
+}
+
 extern "C" {
 
 int ed_owner_map(const ed_plan_t* plan, int R1, const uint8_t* idx, uint8_t* owner, void* stream_) {
@@ -431,7 +462,7 @@ static int launch_epilogue(const ed_plan_t* plan, const ed_step_params_t* d_para
   const ed_plan_t& P = *plan;
   if (!P.mrow_lo || !P.mrow_n || !P.mcol_lo || !P.mcol_n || !P.up_row || !P.up_col || !P.down_row || !P.down_col ||
       !P.views || !P.vrow_first || !P.vrow_cnt || !P.vcol_first || !P.vcol_cnt || !P.row_src || !P.col_src ||
-      !P.pix_ref || !P.cell_cand || !P.cell_down)
+      !P.pix_ref || !P.cell_cand || !P.cell_down || !P.vrow_off || !P.vcol_off)
     return ED_ERR_INVALID;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   // channels per thread: 4 when the batch alone fills the GPU, 1 (channels spread over gridDim.z) for small batches
@@ -442,6 +473,17 @@ static int launch_epilogue(const ed_plan_t* plan, const ed_step_params_t* d_para
   const bool vec = (P.W % 4 == 0) && aligned(latent) && aligned(out_latent) && (!out_x0 || aligned(out_x0)) &&
                    (!noise || aligned(noise));
   const int mode = g_epilogue_mode.load();
+  if (mode == ED_EPILOGUE_AUTO || mode == ED_EPILOGUE_HALF) {
+    int rc = ED_ERR_UNSUPPORTED;
+    switch (out_dtype) {
+      case ED_F32: rc = launch_half<float>(A, stream); break;
+      case ED_F16: rc = launch_half<__half>(A, stream); break;
+      case ED_BF16: rc = launch_half<__nv_bfloat16>(A, stream); break;
+      default: return ED_ERR_INVALID;
+    }
+    if (rc == ED_OK) g_launches_half.fetch_add(1);
+    if (rc != ED_ERR_UNSUPPORTED || mode == ED_EPILOGUE_HALF) return rc;   // forced: no silent fall-back
+  }
   if (mode != ED_EPILOGUE_DIRECT) {
     int rc = ED_ERR_UNSUPPORTED;
     // AUTO: the staged kernel is the throughput shape (a thread carries 4 pixels x 4 channels behind a TMA wait); small
@@ -506,8 +548,13 @@ int ed_epilogue_launch_counts(int64_t* direct, int64_t* staged) {
   return ED_OK;
 }
 
+int ed_epilogue_launch_counts3(int64_t* direct, int64_t* staged, int64_t* half) {
+  if (half) *half = g_launches_half.load();
+  return ed_epilogue_launch_counts(direct, staged);
+}
+
 int ed_set_epilogue_mode(int mode) {
-  if (mode != ED_EPILOGUE_AUTO && mode != ED_EPILOGUE_DIRECT && mode != ED_EPILOGUE_STAGED) return ED_ERR_INVALID;
+  if (mode < ED_EPILOGUE_AUTO || mode > ED_EPILOGUE_HALF) return ED_ERR_INVALID;
   g_epilogue_mode.store(mode);
   return ED_OK;
 }

@@ -21,6 +21,7 @@ import math
 from dataclasses import dataclass, field
 from fractions import Fraction
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -133,13 +134,15 @@ def nearest_index(n_in, n_out):
 def cover_ranges(starts, length, size):
     """For windows [s, s+length) with non-decreasing starts: per position p the first covering window and how many
     consecutive windows cover it."""
-    first, cnt = [0] * size, [0] * size
-    for p in range(size):
-        cov = [k for k, s in enumerate(starts) if s <= p < s + length]
-        if cov:
-            first[p], cnt[p] = cov[0], len(cov)
-            assert cov == list(range(cov[0], cov[0] + len(cov)))
-    return first, cnt
+    st = np.asarray(starts, dtype=np.int64)
+    p = np.arange(size, dtype=np.int64)
+    # windows are sorted by start and share one length, so the windows covering p are the consecutive run
+    # [first index with start + length > p, first index with start > p)
+    lo = np.searchsorted(st + length, p, side="right")
+    hi = np.searchsorted(st, p, side="right")
+    cnt = np.maximum(hi - lo, 0)
+    first = np.where(cnt > 0, lo, 0)
+    return first.tolist(), cnt.tolist()
 
 
 @dataclass
@@ -159,6 +162,7 @@ class WaveGeometry:
     vw: int
     v_pad: tuple            # (l, r, t, b) padding of a view crop inside the canvas
     tables: dict = field(default_factory=dict)   # name -> list[int]
+    flags: int = 0          # PLAN_* bits (ed_plan_t.flags)
 
     @property
     def nv(self):
@@ -200,25 +204,60 @@ def build_geometry(B, C, H, W, native, ds, window, stride, context) -> WaveGeome
     g.tables = dict(row_src=row_src, col_src=col_src, mrow_lo=mrow_lo, mrow_n=mrow_n, mcol_lo=mcol_lo, mcol_n=mcol_n,
                     up_row=up_row, up_col=up_col, down_row=down_row, down_col=down_col,
                     views=vt, vrow_first=vrow_first, vrow_cnt=vrow_cnt, vcol_first=vcol_first, vcol_cnt=vcol_cnt)
+    # per-row / per-column view offsets: with the windows on a grid, the canvas row of latent row y inside the view of the
+    # FIRST covering grid row depends on y only, likewise for columns (used by the exact-1/2 fast-path epilogue)
+    A = lambda v: np.asarray(v, dtype=np.int64)
+    vta = A(vt).reshape(-1, 8)
+    ys, xs = np.arange(H), np.arange(W)
+    vr_first, vc_first = A(vrow_first), A(vcol_first)
+    row_view, col_view = vr_first * nvc, vc_first                       # a view of that grid row / column
+    vrow_off = vtp + vta[row_view, 6] + (ys - vta[row_view, 0])
+    vcol_off = vlp + vta[col_view, 7] + (xs - vta[col_view, 2])
+    g.tables.update(vrow_off=vrow_off.tolist(), vcol_off=vcol_off.tolist())
     # static per-pixel / per-cell references (what the epilogue would otherwise re-derive per pixel, per channel)
-    dir_off = lambda y, x: (tp + up_row[y]) * native + lp + up_col[x]
-    pix = []
-    for y in range(H):
-        for x in range(W):
-            if vrow_cnt[y] == 1 and vcol_cnt[x] == 1:
-                v = vrow_first[y] * nvc + vcol_first[x]
-                h0, _, w0, _, _, _, n_t, n_l = vt[v * 8:v * 8 + 8]
-                voff = (vtp + n_t + (y - h0)) * native + vlp + n_l + (x - w0)
-            else:
-                v, voff = -1, 0
-            pix += [dir_off(y, x), v, voff, up_row[y] * lw + up_col[x]]
-    cand, down = [], []
-    for r in range(lh):
-        for c in range(lw):
-            cand += [row_src[2 * r + (j >> 1)] * W + col_src[2 * c + (j & 1)] for j in range(4)]
-            down += [down_row[r] * W + down_col[c], dir_off(down_row[r], down_col[c])]
-    g.tables.update(pix_ref=pix, cell_cand=cand, cell_down=down)
+    ur, uc = A(up_row), A(up_col)
+    dir_off = ((tp + ur) * native)[:, None] + (lp + uc)[None, :]                                  # (H, W)
+    single = (A(vrow_cnt) == 1)[:, None] & (A(vcol_cnt) == 1)[None, :]
+    view = vr_first[:, None] * nvc + vc_first[None, :]
+    voff = (vrow_off * native)[:, None] + vcol_off[None, :]
+    pix = np.stack([dir_off, np.where(single, view, -1), np.where(single, voff, 0), ur[:, None] * lw + uc[None, :]], axis=-1)
+    rs, cs = A(row_src), A(col_src)
+    r, c = np.arange(lh), np.arange(lw)
+    cand = np.stack([(rs[2 * r + (j >> 1)] * W)[:, None] + cs[2 * c + (j & 1)][None, :] for j in range(4)], axis=-1)
+    dr, dc = A(down_row), A(down_col)
+    down = np.stack([(dr * W)[:, None] + dc[None, :], dir_off[dr][:, dc]], axis=-1)
+    g.tables.update(pix_ref=pix.reshape(-1).tolist(), cell_cand=cand.reshape(-1).tolist(), cell_down=down.reshape(-1).tolist())
+    g.flags = PLAN_HALF_FAST if _half_fast(g, H, W, native, lh, lw, rs, cs, ur, uc, dr, dc, A(mrow_lo), A(mrow_n), A(mcol_lo),
+                                            A(mcol_n), A(vrow_cnt), A(vcol_cnt), vr_first, vc_first, vrow_off, vcol_off,
+                                            tp, lp) else 0
     return g
+
+
+PLAN_HALF_FAST = 1   # ED_PLAN_HALF_FAST of include/elastic_b200.h
+
+
+def _half_fast(g, H, W, native, lh, lw, rs, cs, ur, uc, dr, dc, mrow_lo, mrow_n, mcol_lo, mcol_n, vrow_cnt, vcol_cnt,
+               vr_first, vc_first, vrow_off, vcol_off, tp, lp):
+    """True when the plan is the exact 1/2-ratio geometry with tiling views that the fast-path epilogue kernels index
+    arithmetically (every tiled BASELINE config).  The C ABI documents this list at ED_PLAN_HALF_FAST; the kernels trust
+    the flag, so every identity is checked here."""
+    if g.C != 4 or H % 2 or W % 8 or 2 * lh != H or 2 * lw != W or native % 8 or lp % 4:
+        return False
+    ys, xs = np.arange(H), np.arange(W)
+    ok = (np.array_equal(ur, ys >> 1) and np.array_equal(uc, xs >> 1)              # nearest-up reads cell (y/2, x/2)
+          and np.array_equal(rs, ys) and np.array_equal(cs, xs)                    # the 2x-resized grid IS the latent
+          and np.array_equal(dr, 2 * np.arange(lh)) and np.array_equal(dc, 2 * np.arange(lw))   # nearest-down reads (2r, 2c)
+          and np.array_equal(mrow_lo, ys) and np.all(mrow_n == 1)                  # restored mask = resized mask
+          and np.array_equal(mcol_lo, xs) and np.all(mcol_n == 1)
+          and np.all(vrow_cnt == 1) and np.all(vcol_cnt == 1))                     # every pixel under exactly one window
+    if not ok:
+        return False
+    # the two rows of a row pair lie in the same view on consecutive canvas rows
+    if not (np.array_equal(vr_first[0::2], vr_first[1::2]) and np.array_equal(vrow_off[0::2] + 1, vrow_off[1::2])):
+        return False
+    # every aligned group of 8 columns lies in one view, contiguous, starting at a canvas column that is a multiple of 8
+    vc8, vo8 = vc_first.reshape(-1, 8), vcol_off.reshape(-1, 8)
+    return bool(np.all(vc8 == vc8[:, :1]) and np.all(vo8 == vo8[:, :1] + np.arange(8)) and np.all(vo8[:, 0] % 8 == 0))
 
 
 @dataclass

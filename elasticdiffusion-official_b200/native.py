@@ -17,8 +17,9 @@ SOURCES = ["abi.cu", "gather.cu", "epilogue.cu", "tiles.cu"]
 ED_MAX_RENOISE = 1000
 ED_F32, ED_F16, ED_BF16 = 0, 1, 2
 FLAG_RENOISE, FLAG_RRG, FLAG_FP16_SEM = 1, 2, 4
-EPILOGUE_AUTO, EPILOGUE_DIRECT, EPILOGUE_STAGED = 0, 1, 2
-ABI_VERSION = 3
+EPILOGUE_AUTO, EPILOGUE_DIRECT, EPILOGUE_STAGED, EPILOGUE_HALF = 0, 1, 2, 3
+PLAN_HALF_FAST = 1
+ABI_VERSION = 4
 
 
 class NativeError(RuntimeError):
@@ -29,11 +30,11 @@ class Plan(C.Structure):
     """ed_plan_t"""
     _fields_ = [(n, C.c_int32) for n in
                 ("B", "C", "H", "W", "dH", "dW", "lh", "lw", "g_tp", "g_lp", "nv", "nvr", "nvc", "vh", "vw",
-                 "v_tp", "v_lp", "reserved0")] + \
+                 "v_tp", "v_lp", "flags")] + \
                [(n, C.c_void_p) for n in
                 ("row_src", "col_src", "mrow_lo", "mrow_n", "mcol_lo", "mcol_n", "up_row", "up_col", "down_row",
                  "down_col", "views", "vrow_first", "vrow_cnt", "vcol_first", "vcol_cnt", "pix_ref", "cell_cand",
-                 "cell_down")]
+                 "cell_down", "vrow_off", "vcol_off")]
 
 
 class StepParams(C.Structure):
@@ -68,6 +69,7 @@ EXPORTS = {
                                         C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ed_set_epilogue_mode": (C.c_int, [C.c_int]),
     "ed_epilogue_launch_counts": (C.c_int, [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "ed_epilogue_launch_counts3": (C.c_int, [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "ed_renoise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ed_gather_cond": (C.c_int, [C.POINTER(Plan), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_int, C.c_void_p]),
@@ -83,6 +85,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/*.cu into libelastic_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
     srcs = [os.path.join(_HERE, "csrc", s) for s in SOURCES]
     deps = srcs + [os.path.join(_HERE, "csrc", "common.cuh"), os.path.join(_HERE, "csrc", "epilogue_staged.cuh"),
+                   os.path.join(_HERE, "csrc", "epilogue_half.cuh"),
                    os.path.join(_ROOT, "include", "elastic_b200.h")]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
@@ -125,10 +128,10 @@ def check(status: int, what: str = "") -> None:
 
 
 def epilogue_launch_counts():
-    """(direct, staged): how many wave-epilogue launches of this process took each kernel."""
-    d, s = C.c_int64(0), C.c_int64(0)
-    check(lib().ed_epilogue_launch_counts(C.byref(d), C.byref(s)), "ed_epilogue_launch_counts")
-    return d.value, s.value
+    """(direct, staged, half): how many wave-epilogue launches of this process took each kernel."""
+    d, s, h = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    check(lib().ed_epilogue_launch_counts3(C.byref(d), C.byref(s), C.byref(h)), "ed_epilogue_launch_counts3")
+    return d.value, s.value, h.value
 
 
 def ptr(t):
@@ -143,6 +146,19 @@ def dtype_code(dt):
 def stream_handle():
     import torch
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def plan_from_geometry(geo, device, flags=None):
+    """(ed_plan_t, keep): uploads the int32 tables of a `geometry.WaveGeometry` to `device` and fills the struct; `keep`
+    holds the table tensors and must outlive every launch that uses the plan.  `flags`: override of geo.flags (tests)."""
+    import torch
+    keep = {k: torch.tensor(v if len(v) else [0], dtype=torch.int32, device=device) for k, v in geo.tables.items()}
+    lp, rp, tp, bp = geo.g_pad
+    vlp, vrp, vtp, vbp = geo.v_pad
+    plan = Plan(B=geo.B, C=geo.C, H=geo.H, W=geo.W, dH=geo.native, dW=geo.native, lh=geo.lh, lw=geo.lw, g_tp=tp, g_lp=lp,
+                nv=geo.nv, nvr=geo.nvr, nvc=geo.nvc, vh=geo.vh, vw=geo.vw, v_tp=vtp, v_lp=vlp,
+                flags=geo.flags if flags is None else flags, **{k: v.data_ptr() for k, v in keep.items()})
+    return plan, keep
 
 
 def strips_array(strips):

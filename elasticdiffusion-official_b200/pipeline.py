@@ -516,14 +516,7 @@ class ElasticDiffusion(nn.Module):
         native.lib()
 
     def _upload_plan(self, geo):
-        dev = self.device
-        keep = {k: _i32(dev, v) for k, v in geo.tables.items()}
-        lp, rp, tp, bp = geo.g_pad
-        vlp, vrp, vtp, vbp = geo.v_pad
-        plan = native.Plan(B=geo.B, C=geo.C, H=geo.H, W=geo.W, dH=geo.native, dW=geo.native, lh=geo.lh, lw=geo.lw,
-                           g_tp=tp, g_lp=lp, nv=geo.nv, nvr=geo.nvr, nvc=geo.nvc, vh=geo.vh, vw=geo.vw, v_tp=vtp,
-                           v_lp=vlp, **{k: v.data_ptr() for k, v in keep.items()})
-        return plan, keep
+        return native.plan_from_geometry(geo, self.device)
 
     def _dist(self):
         import torch.distributed as dist

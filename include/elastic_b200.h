@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ED_ABI_VERSION 3
+#define ED_ABI_VERSION 4
 #define ED_MAX_RENOISE 1000
 
 typedef enum {
@@ -52,7 +52,7 @@ typedef struct {
   int32_t nv, nvr, nvc;     /* number of views, view-grid rows, view-grid cols (view i = r*nvc + c) */
   int32_t vh, vw;           /* view crop size (window + context), same for all views */
   int32_t v_tp, v_lp;       /* top/left offset of a view crop inside the canvas (0 unless view < native) */
-  int32_t reserved0;
+  int32_t flags;            /* ED_PLAN_* : properties of the geometry the CALLER has verified on the host (0 = none) */
   const int32_t* row_src;   /* [2*lh] latent row feeding each row of the 2x-resized grid (ed:585-589,612) */
   const int32_t* col_src;   /* [2*lw] */
   const int32_t* mrow_lo;   /* [H] first resized row OR-ed into latent row y of the restored mask (ed:446-465) */
@@ -76,7 +76,24 @@ typedef struct {
   const int32_t* cell_cand; /* [lh*lw*4] latent-plane offsets of the 4 candidate pixels of each 2x2 cell (ed:612-613) */
   const int32_t* cell_down; /* [lh*lw*2] pixel index Y*W+X that nearest-DOWNsampling reads for the cell (ed:688), and
                                the dir_off of that pixel */
+  /* per-row / per-column view offsets (the windows form a grid): canvas row of latent row y inside the view of the
+   * first covering grid row = v_tp + n_t + (y - h0), and the same per column; offset of pixel (y, x) in that view's
+   * canvas plane = vrow_off[y]*dW + vcol_off[x] */
+  const int32_t* vrow_off;  /* [H] */
+  const int32_t* vcol_off;  /* [W] */
 } ed_plan_t;
+
+/* ED_PLAN_HALF_FAST - the exact 1/2-ratio geometry with tiling views (every tiled BASELINE config: SD2.1 512x1024, SDXL
+ * 1024x2048, SDXL 2048x2048).  The caller asserts ALL of:
+ *   C == 4, H even, W % 8 == 0, lh*2 == H, lw*2 == W, dW % 8 == 0, g_lp % 4 == 0;
+ *   up_row[y] == y/2, up_col[x] == x/2; row_src[i] == i, col_src[i] == i (the 2x-resized grid is the latent itself);
+ *   down_row[r] == 2r, down_col[c] == 2c; mrow_lo[y] == y, mrow_n[y] == 1, mcol_lo[x] == x, mcol_n[x] == 1;
+ *   every pixel is covered by exactly one view window (vrow_cnt == vcol_cnt == 1 everywhere);
+ *   rows 2r and 2r+1 lie in the same view on consecutive canvas rows; every aligned group of 8 columns lies in one view,
+ *   contiguous, starting at a canvas column that is a multiple of 8 (vcol_off[8j] % 8 == 0).
+ * With it, ed_wave_epilogue[_peer] derives every index arithmetically from (y, x) instead of loading the per-pixel
+ * reference tables (the "half" kernels, csrc/epilogue_half.cuh).  Results are bit-identical with and without the flag. */
+#define ED_PLAN_HALF_FAST 1
 
 /* Per-wave scalars, read by the epilogue kernel from DEVICE memory so that a captured CUDA graph can be replayed
  * with new values (upload with ed_upload_step_params or any memcpy). */
@@ -158,13 +175,15 @@ int ed_wave_epilogue(const ed_plan_t* plan, const ed_step_params_t* d_params, in
                      const void* unet_out, int out_dtype, const uint8_t* idx, const uint8_t* owner,
                      const float* noise, float* out_latent, float* out_x0, void* stream);
 
-/* Kernel selection of ed_wave_epilogue, process-wide (tests / A-B measurements): AUTO as described above, DIRECT never
- * stages, STAGED returns ED_ERR_UNSUPPORTED instead of falling back. */
-typedef enum { ED_EPILOGUE_AUTO = 0, ED_EPILOGUE_DIRECT = 1, ED_EPILOGUE_STAGED = 2 } ed_epilogue_mode;
+/* Kernel selection of ed_wave_epilogue, process-wide (tests / A-B measurements): AUTO = the half kernels when the plan
+ * carries ED_PLAN_HALF_FAST (and the launch is in their domain), else staged / direct as described above; DIRECT and
+ * STAGED never take the half kernels; STAGED and HALF return ED_ERR_UNSUPPORTED instead of falling back. */
+typedef enum { ED_EPILOGUE_AUTO = 0, ED_EPILOGUE_DIRECT = 1, ED_EPILOGUE_STAGED = 2, ED_EPILOGUE_HALF = 3 } ed_epilogue_mode;
 int ed_set_epilogue_mode(int mode);
 /* Process-wide number of ed_wave_epilogue / ed_wave_epilogue_peer launches that took the direct and the staged kernel
- * (diagnostics: which kernel AUTO chose; either pointer may be NULL). */
+ * (diagnostics: which kernel AUTO chose; either pointer may be NULL); ed_epilogue_launch_counts3 adds the half kernels. */
 int ed_epilogue_launch_counts(int64_t* direct, int64_t* staged);
+int ed_epilogue_launch_counts3(int64_t* direct, int64_t* staged, int64_t* half);
 
 /* ---- C1: the same epilogue fused with the multi-GPU exchange ---------------------------------
  * With wave samples sharded over `world` ranks (rank r holds samples [r*per, (r+1)*per) of the wave layout in its own

@@ -6,6 +6,7 @@
 #include <mutex>
 #include <vector>
 
+#include "epilogue_half.cuh"
 #include "epilogue_staged.cuh"
 
 thread_local dim3 threadIdx, blockIdx;
@@ -96,6 +97,48 @@ extern "C" int emu_wave_epilogue(const ed_plan_t* plan, const ed_step_params_t* 
     case ED_F32: return run<float>(A, 4, sms, info);
     case ED_F16: return run<__half>(A, 2, sms, info);
     case ED_BF16: return run<__nv_bfloat16>(A, 2, sms, info);
+  }
+  return ED_ERR_INVALID;
+}
+
+// ---- half kernels (csrc/epilogue_half.cuh): no barrier, no TMA -> the threads of a CTA run one after the other --------------
+template <typename OT, bool MULTI, bool PEER>
+static int run_half_as(const ed::EpiArgs& A, int so, int* info) {
+  const ed::HalfCfg cfg = ed::half_config(A.P, A.R1, so);
+  if (!cfg.ok || A.noise) return ED_ERR_UNSUPPORTED;
+  std::vector<uint8_t> smem(cfg.smem + 128);
+  ed::emu_dyn_smem = smem.data();
+  blockDim = dim3(cfg.bx, cfg.by, 1);
+  gridDim = dim3(cfg.grid_x, cfg.grid_y, info && info[0] > 0 ? (unsigned)info[0] : (unsigned)cfg.grid_z);   // test hook: short grid z
+  if (info) { info[1] = cfg.bx; info[2] = cfg.by; info[3] = (int)cfg.smem; info[4] = cfg.grid_x * cfg.grid_y * cfg.grid_z; }
+  for (unsigned bz = 0; bz < gridDim.z; ++bz)
+    for (unsigned by = 0; by < gridDim.y; ++by)
+      for (unsigned bx = 0; bx < gridDim.x; ++bx) {
+        memset(smem.data(), 0xA5, smem.size());
+        blockIdx = dim3(bx, by, bz);
+        for (unsigned t = 0; t < blockDim.x * blockDim.y; ++t) {
+          threadIdx = dim3(t % blockDim.x, t / blockDim.x, 0);
+          ed::wave_epilogue_half_kernel<OT, MULTI, PEER>(A);
+        }
+      }
+  return ED_OK;
+}
+
+template <typename OT>
+static int run_half(const ed::EpiArgs& A, int so, int* info) {
+  if (A.peers) return A.R1 > 1 ? run_half_as<OT, true, true>(A, so, info) : run_half_as<OT, false, true>(A, so, info);
+  return A.R1 > 1 ? run_half_as<OT, true, false>(A, so, info) : run_half_as<OT, false, false>(A, so, info);
+}
+
+// peers != NULL: HOST array of `world` buffer pointers (the multi-GPU entry point's sample -> rank mapping)
+extern "C" int emu_wave_epilogue_half(const ed_plan_t* plan, const ed_step_params_t* params, int R1, const float* latent,
+                                      const void* unet_out, const void* const* peers, int world, int per, int out_dtype,
+                                      const uint8_t* idx, const uint8_t* owner, float* out_latent, float* out_x0, int* info) {
+  ed::EpiArgs A{*plan, params, latent, unet_out, peers, world, per, idx, owner, nullptr, out_latent, out_x0, R1};
+  switch (out_dtype) {
+    case ED_F32: return run_half<float>(A, 4, info);
+    case ED_F16: return run_half<__half>(A, 2, info);
+    case ED_BF16: return run_half<__nv_bfloat16>(A, 2, info);
   }
   return ED_ERR_INVALID;
 }

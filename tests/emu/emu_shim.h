@@ -35,6 +35,7 @@ struct float4 { float x, y, z, w; };
 struct int4 { int x, y, z, w; };
 struct int2 { int x, y; };
 struct uint2 { unsigned x, y; };
+struct uint4 { unsigned x, y, z, w; };
 struct uchar4 { unsigned char x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 
@@ -62,6 +63,7 @@ static inline float __frcp_rn(float a) { return 1.0f / a; }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 void __syncthreads();
 
+// (epilogue_half.cuh needs no barrier / TMA: its emulation runs the threads of a CTA one after the other)
 // path-coverage counters: 0 staged threads, 1 unstaged threads, 2 RRG down-cell inside the boxes, 3 outside (global load),
 // 4 vector view loads, 5 scalar single-view loads, 6 multi-cover walks
 extern std::atomic<long long> ed_emu_counters[8];

@@ -13,14 +13,8 @@ geometry, native = PKG.geometry, PKG.native
 DEV = "cuda"
 
 
-def upload(geo):
-    keep = {k: torch.tensor(v if len(v) else [0], dtype=torch.int32, device=DEV) for k, v in geo.tables.items()}
-    lp, rp, tp, bp = geo.g_pad
-    vlp, vrp, vtp, vbp = geo.v_pad
-    plan = native.Plan(B=geo.B, C=geo.C, H=geo.H, W=geo.W, dH=geo.native, dW=geo.native, lh=geo.lh, lw=geo.lw,
-                       g_tp=tp, g_lp=lp, nv=geo.nv, nvr=geo.nvr, nvc=geo.nvc, vh=geo.vh, vw=geo.vw, v_tp=vtp, v_lp=vlp,
-                       **{k: v.data_ptr() for k, v in keep.items()})
-    return plan, keep
+def upload(geo, flags=None):
+    return native.plan_from_geometry(geo, DEV, flags)
 
 
 def make_strips(geo, inner_h, inner_w, seed):
@@ -89,10 +83,11 @@ def test_gather_kernels_match_spec(cfg, dtype):
 
 @pytest.fixture
 def epilogue_kernel(request):
-    """direct = scattered-load kernel, staged = TMA tile-staged kernel (forced: an unsupported shape is an error, not a
-    silent fall-back to the other kernel)."""
+    """direct = scattered-load kernel, staged = TMA tile-staged kernel, half = exact-1/2-ratio kernels (forced: an
+    unsupported shape is an error, not a silent fall-back to another kernel)."""
     L = native.lib()
-    native.check(L.ed_set_epilogue_mode({"direct": native.EPILOGUE_DIRECT, "staged": native.EPILOGUE_STAGED}[request.param]))
+    native.check(L.ed_set_epilogue_mode({"direct": native.EPILOGUE_DIRECT, "staged": native.EPILOGUE_STAGED,
+                                         "half": native.EPILOGUE_HALF}[request.param]))
     yield request.param
     native.check(L.ed_set_epilogue_mode(native.EPILOGUE_AUTO))
 
@@ -105,16 +100,23 @@ def test_wave_epilogue_matches_spec(cfg, mode, dtype, epilogue_kernel, R1=None):
     _epilogue_case(cfg, mode, dtype, R1)
 
 
-def _epilogue_case(cfg, mode, dtype, R1=None, peer_world=None):
+def _epilogue_case(cfg, mode, dtype, R1=None, peer_world=None, plan_flags=None, poison=False):
     """One fused-epilogue launch against the contract emulation.  `peer_world`: go through ed_wave_epilogue_peer with the
     wave's samples split over `peer_world` per-"rank" buffers (sample s lives in buffer s // per at index s % per) - the
     multi-GPU entry point exercised on ONE GPU: the pointer table simply points at separate local allocations."""
     L = native.lib()
     geo = build(cfg)
-    plan, keep = upload(geo)
+    plan, keep = upload(geo, plan_flags)
     R1 = R1 or (1 if (mode == "rrg" and cfg[0] == 2) else 4)
     torch.manual_seed(1)
     x = torch.randn(geo.B, geo.C, geo.H, geo.W, device=DEV)
+    if poison:      # quotients outside the reciprocal division's range (inf, nan, overflow): IEEE-division results expected
+        flat = x.view(-1)
+        where = torch.randperm(flat.numel(), device=DEV)[:64]
+        flat[where[:16]] = float("inf")
+        flat[where[16:32]] = -float("inf")
+        flat[where[32:48]] = 1e38
+        flat[where[48:]] = float("nan")
     idx = rand_idx(R1, geo.lh * geo.lw, 5)
     n = 2 * geo.B * R1 + geo.nv * geo.B
     out = torch.randn(n, geo.C, geo.native, geo.native, device=DEV).to(dtype)
@@ -163,15 +165,74 @@ def _epilogue_case(cfg, mode, dtype, R1=None, peer_world=None):
                                              native.ptr(x0), st))
     torch.cuda.synchronize()
     want, want_x0 = ws.spec_epilogue(geo, prm, x, out, idx, noise)
+    if poison:      # nan payloads are not compared
+        for got, ref in ((x0, want_x0), (y, want)):
+            assert torch.equal(torch.isnan(got), torch.isnan(ref))
+            assert torch.equal(torch.nan_to_num(got, nan=0.0, posinf=3e38, neginf=-3e38), torch.nan_to_num(ref, nan=0.0, posinf=3e38, neginf=-3e38))
+            assert torch.equal(torch.isinf(got), torch.isinf(ref))
+        return y
     assert torch.equal(x0, want_x0), f"x0 max diff {(x0 - want_x0).abs().max().item():.3e}"
     assert torch.equal(y, want), f"latent max diff {(y - want).abs().max().item():.3e}"
+    return y
+
+
+# plans that carry ED_PLAN_HALF_FAST (exact 1/2 ratio, tiling views)
+HALF_GEOS = [GEOS[0], GEOS[1], GEOS[3], GEOS[8], GEOS[9],
+             (3, 32, 48, 64, (16, 24), 32),          # narrow: 6 column groups (guard lanes), low-res latent at g_lp = 20
+             (24, 128, 256, 128, (64, 128), 64)]     # a batch that fills the GPU several times over
+
+
+@pytest.mark.parametrize("cfg", HALF_GEOS)
+@pytest.mark.parametrize("mode", ["plain", "rrg"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("R1", [1, 4, 8])
+@pytest.mark.parametrize("epilogue_kernel", ["half"], indirect=True)
+def test_half_epilogue_matches_spec(cfg, mode, dtype, R1, epilogue_kernel):
+    """the half kernels (csrc/epilogue_half.cuh), forced: R1 == 1 streaming kernel and R1 > 1 per-thread-slot kernel."""
+    assert build(cfg).flags & native.PLAN_HALF_FAST
+    h0 = native.epilogue_launch_counts()[2]
+    _epilogue_case(cfg, mode, dtype, R1=R1)
+    assert native.epilogue_launch_counts()[2] == h0 + 1
+
+
+@pytest.mark.parametrize("epilogue_kernel", ["half"], indirect=True)
+def test_half_mode_refuses_what_it_cannot_do(epilogue_kernel):
+    with pytest.raises(native.NativeError):
+        _epilogue_case(GEOS[5], "plain", torch.float32, R1=2)         # general ratio: no ED_PLAN_HALF_FAST
+    with pytest.raises(native.NativeError):
+        _epilogue_case(GEOS[0], "renoise", torch.bfloat16, R1=4)      # noise stream: the staged kernel's job
+
+
+@pytest.mark.parametrize("cfg,mode,R1,world", [(GEOS[0], "rrg", 1, 8), (GEOS[0], "plain", 1, 4), (GEOS[0], "rrg", 8, 8),
+                                               (GEOS[3], "rrg", 1, 8), (GEOS[1], "plain", 5, 3), (GEOS[9], "rrg", 1, 2)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("epilogue_kernel", ["half"], indirect=True)
+def test_half_epilogue_peer_matches_spec_on_one_gpu(cfg, mode, R1, world, dtype, epilogue_kernel):
+    _epilogue_case(cfg, mode, dtype, R1=R1, peer_world=world)
+
+
+@pytest.mark.parametrize("epilogue_kernel", ["half", "staged", "direct"], indirect=True)
+def test_non_finite_quotients_follow_ieee_division(epilogue_kernel):
+    """inf / nan / overflowing quotients: the reciprocal-based division of the staged and half kernels must fall back to
+    IEEE division (per quotient in the staged kernel, per tile in the half kernels)."""
+    for mode, R1 in (("plain", 1), ("rrg", 1), ("rrg", 3)):
+        _epilogue_case(GEOS[1], mode, torch.bfloat16, R1=R1, poison=True)
+
+
+def test_plan_flag_does_not_change_results():
+    """AUTO with and without ED_PLAN_HALF_FAST on the same inputs: bit-identical outputs (different kernels)."""
+    for mode, R1 in (("plain", 1), ("rrg", 1), ("rrg", 8)):
+        a = _epilogue_case(GEOS[0], mode, torch.bfloat16, R1=R1)
+        b = _epilogue_case(GEOS[0], mode, torch.bfloat16, R1=R1, plan_flags=0)
+        assert torch.equal(a, b)
 
 
 @pytest.mark.parametrize("cfg", [GEOS[0], GEOS[3], GEOS[4], GEOS[5], GEOS[8], GEOS[9]])
 @pytest.mark.parametrize("mode", ["plain", "renoise", "rrg"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("world", [2, 3, 8])
-def test_wave_epilogue_peer_matches_spec_on_one_gpu(cfg, mode, dtype, world):
+@pytest.mark.parametrize("epilogue_kernel", ["direct"], indirect=True)    # the generic PEER kernel (AUTO would take the half
+def test_wave_epilogue_peer_matches_spec_on_one_gpu(cfg, mode, dtype, world, epilogue_kernel):   # kernels where flagged)
     """ed_wave_epilogue_peer (the PEER = true instantiation that the N-GPU pipeline launches) with world in {2, 3, 8}:
     ragged `per`, idle ranks (world 8 with 12 samples -> ranks 6, 7 own nothing), bit-exact against the same spec."""
     _epilogue_case(cfg, mode, dtype, R1=(1 if mode == "rrg" and cfg[0] == 2 else 4), peer_world=world)

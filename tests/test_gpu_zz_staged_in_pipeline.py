@@ -1,7 +1,8 @@
-"""GPU: the product path at a batch large enough for AUTO to choose the TMA tile-staged epilogue (both of its
-instantiations: wave 1 with the re-noise stream, wave 2 without), against the oracle port executed eagerly on the same
-device.  (At the BASELINE shapes with one prompt every launch is small and AUTO keeps the direct kernel; the staged kernel
-is otherwise covered kernel-by-kernel in test_gpu_kernels.py.)  Runs last (file name) on purpose."""
+"""GPU: the product path at a batch large enough for AUTO to choose the TMA tile-staged epilogue for the re-noise wave,
+with the half kernels (exact 1/2 ratio, plan flag ED_PLAN_HALF_FAST) serving the launches without a noise stream, against
+the oracle port executed eagerly on the same device.  (At the BASELINE shapes with one prompt the re-noise launch is small
+and AUTO keeps the direct kernel for it; every kernel is otherwise covered one by one in test_gpu_kernels.py.)  Runs last
+(file name) on purpose."""
 import pytest
 import torch
 
@@ -34,21 +35,29 @@ def test_large_batch_takes_the_staged_epilogue_and_matches_the_oracle():
     ed = make_ed("2.1", 8, "cuda")
     ed.autocast = False
     ed.seed_everything(3)
-    d0, s0 = PKG.native.epilogue_launch_counts()
+    d0, s0, h0 = PKG.native.epilogue_launch_counts()
     lat, _ = ed.denoise(**kw, progress=lambda it: it)
-    d1, s1 = PKG.native.epilogue_launch_counts()
-    assert s1 - s0 == 3 and d1 == d0, f"expected 3 staged epilogue launches (2 waves + 1), got staged {s1 - s0}, direct {d1 - d0}"
+    d1, s1, h1 = PKG.native.epilogue_launch_counts()
+    # step 0: wave 1 + re-noise -> staged, wave 2 + RRG (R1 = 1) -> half; step 1 (last, no repaint, R1 = 3) -> half
+    assert (s1 - s0, h1 - h0, d1 - d0) == (1, 2, 0), f"staged {s1 - s0}, half {h1 - h0}, direct {d1 - d0}"
     mse = torch.mean((lat - ref) ** 2).item()
     assert mse < 1e-8, f"mse {mse:.3e} max {(lat - ref).abs().max().item():.3e}"
 
 
 def test_error_behaviour_of_the_cuda_path_matches_the_reference():
-    """ed:200-201: sizes that are not multiples of 8 -> TypeError (the reference raises a str), before any kernel runs;
-    a condition image without a ControlNet -> ValueError."""
+    """Sizes that are not multiples of 8 are floored like the reference does (ed:998 draws a (height // 8, width // 8)
+    latent; only get_views() itself raises, ed:200-201); a condition image without a ControlNet -> ValueError."""
     ed = make_ed("2.1", 4, "cuda")
+    ed.rng_device = torch.device("cpu")
+    ed.seed_everything(5)
+    # 516 x 1028 floors to the 64 x 128 latent and the (32, 64) low-res size of 512 x 1024 (checked against the live
+    # reference in tests/test_oracle_vs_reference.py::test_sizes_not_divisible_by_8_are_floored)
+    a, _ = ed.denoise("a", "b", height=516, width=1028, num_inference_steps=2, resampling_steps=1, progress=lambda it: it)
+    ed.seed_everything(5)
+    b, _ = ed.denoise("a", "b", height=512, width=1024, num_inference_steps=2, resampling_steps=1, progress=lambda it: it)
+    assert a.shape == (1, 4, 64, 128) and torch.equal(a, b)
     with pytest.raises(TypeError):
-        ed.generate_image("a", "b", height=515, width=512, num_inference_steps=1, resampling_steps=0, progress=lambda it: it)
+        ed.get_views(515, 512)
     with pytest.raises(ValueError):
         ed.denoise("a", "b", height=512, width=512, num_inference_steps=1, resampling_steps=0, progress=lambda it: it,
                    condition_image=torch.rand(1, 3, 512, 512))
-    assert ed.last_run["kernel_launches"] == 0

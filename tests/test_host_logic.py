@@ -26,12 +26,12 @@ def test_library_loads_and_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/elastic_b200.h but not exported"
     assert declared == set(native.EXPORTS), "ctypes binding and header disagree"
     L = native.lib()
-    assert L.ed_abi_version() == native.ABI_VERSION == 3
+    assert L.ed_abi_version() == native.ABI_VERSION == 4
     assert L.ed_strerror(-2).decode().startswith("unsupported")
 
 
 def test_epilogue_entry_points_reject_null_arguments_without_a_gpu():
-    """argument marshalling of the ABI v3 signatures (R1 after d_params; peer variant: pointer table, world, per): invalid
+    """argument marshalling of the ABI v4 signatures (R1 after d_params; peer variant: pointer table, world, per): invalid
     arguments are refused on the host before any CUDA call, so this runs without a device."""
     L = native.lib()
     st = ctypes.c_void_p(0)
@@ -44,13 +44,13 @@ def test_epilogue_entry_points_reject_null_arguments_without_a_gpu():
     assert L.ed_wave_epilogue(ctypes.byref(plan), p, 0, p, p, 0, p, p, None, p, None, st) == -1
     assert L.ed_wave_epilogue(ctypes.byref(plan), p, 256, p, p, 0, p, p, None, p, None, st) == -1
     assert L.ed_wave_epilogue_peer(ctypes.byref(plan), p, 1, p, p, 0, 0, 0, p, p, None, p, None, st) == -1
-    assert L.ed_set_epilogue_mode(3) == -1 and L.ed_set_epilogue_mode(native.EPILOGUE_AUTO) == 0
-    assert native.epilogue_launch_counts() == (0, 0)
+    assert L.ed_set_epilogue_mode(4) == -1 and L.ed_set_epilogue_mode(native.EPILOGUE_AUTO) == 0
+    assert native.epilogue_launch_counts() == (0, 0, 0)
 
 
 def test_struct_layouts_match_header_sizes():
-    # ed_plan_t: 18 int32 + 18 pointers ; ed_step_params_t: 7 float + 5 int32 + 2*ED_MAX_RENOISE float ; ed_tiles_t: 10 int32 + 5 ptr
-    assert ctypes.sizeof(native.Plan) == 18 * 4 + 18 * 8
+    # ed_plan_t: 18 int32 + 20 pointers ; ed_step_params_t: 7 float + 5 int32 + 2*ED_MAX_RENOISE float ; ed_tiles_t: 10 int32 + 5 ptr
+    assert ctypes.sizeof(native.Plan) == 18 * 4 + 20 * 8
     assert ctypes.sizeof(native.StepParams) == (7 + 5 + 2000) * 4
     assert ctypes.sizeof(native.Tiles) == 10 * 4 + 5 * 8
 

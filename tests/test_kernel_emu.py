@@ -22,6 +22,7 @@ EMU_LIB = os.path.join(EMU_DIR, "_build", "libed_emu.so")
 def emu():
     srcs = [os.path.join(EMU_DIR, "emu_epilogue.cpp"), os.path.join(EMU_DIR, "emu_shim.h"),
             os.path.join(ROOT, "elasticdiffusion-official_b200", "csrc", "epilogue_staged.cuh"),
+            os.path.join(ROOT, "elasticdiffusion-official_b200", "csrc", "epilogue_half.cuh"),
             os.path.join(ROOT, "include", "elastic_b200.h")]
     os.makedirs(os.path.dirname(EMU_LIB), exist_ok=True)
     if not os.path.exists(EMU_LIB) or any(os.path.getmtime(EMU_LIB) < os.path.getmtime(s) for s in srcs):
@@ -34,17 +35,14 @@ def emu():
     lib.emu_wave_epilogue.restype = ctypes.c_int
     lib.emu_wave_epilogue.argtypes = [ctypes.POINTER(native.Plan), ctypes.POINTER(native.StepParams), ctypes.c_int] + \
         [ctypes.c_void_p] * 2 + [ctypes.c_int] + [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    lib.emu_wave_epilogue_half.restype = ctypes.c_int
+    lib.emu_wave_epilogue_half.argtypes = [ctypes.POINTER(native.Plan), ctypes.POINTER(native.StepParams), ctypes.c_int] + \
+        [ctypes.c_void_p] * 3 + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 4 + [ctypes.POINTER(ctypes.c_int)]
     return lib
 
 
-def host_plan(geo):
-    keep = {k: torch.tensor(v if len(v) else [0], dtype=torch.int32) for k, v in geo.tables.items()}
-    lp, rp, tp, bp = geo.g_pad
-    vlp, vrp, vtp, vbp = geo.v_pad
-    plan = native.Plan(B=geo.B, C=geo.C, H=geo.H, W=geo.W, dH=geo.native, dW=geo.native, lh=geo.lh, lw=geo.lw,
-                       g_tp=tp, g_lp=lp, nv=geo.nv, nvr=geo.nvr, nvc=geo.nvc, vh=geo.vh, vw=geo.vw, v_tp=vtp, v_lp=vlp,
-                       **{k: v.data_ptr() for k, v in keep.items()})
-    return plan, keep
+def host_plan(geo, flags=None):
+    return native.plan_from_geometry(geo, "cpu", flags)
 
 
 # (B, H, W, native, ds, window) - W % 4 == 0 (the staged kernel's domain; other widths take the direct kernel)
@@ -147,3 +145,94 @@ def test_reciprocal_division_equals_ieee_division(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([exe, "20000"], capture_output=True, text=True)
     assert r.returncode == 0 and " 0 mismatches" in r.stdout, r.stdout
+
+
+# ---- half kernels (csrc/epilogue_half.cuh): plans that carry ED_PLAN_HALF_FAST -------------------------------------------
+HALF_GEOS = [(1, 128, 256, 128, (64, 128), 64),     # cfg3
+             (1, 64, 128, 64, (32, 64), 32),        # cfg2
+             (1, 256, 256, 128, (128, 128), 64),    # cfg4
+             (2, 96, 256, 128, (48, 128), 64),      # window collapse: padded views (v_tp = 16), B = 2
+             (1, 128, 256, 128, (64, 128), 32),     # patch_size 32: 4 x 8 windows
+             (3, 32, 48, 64, (16, 24), 32)]         # narrow: W / 8 = 6 column groups (guard lanes), low-res latent padded (g_lp = 20)
+
+
+def run_half_case(emu, cfg, mode, dtype, R1, world=None, grid_z=0, x0_out=True, poison=False):
+    B, H, W, nat, ds, window = cfg
+    geo = geometry.build_geometry(B, 4, H, W, nat, ds, window, window, nat - window)
+    assert geo.flags & native.PLAN_HALF_FAST, cfg
+    plan, keep = host_plan(geo)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(B, 4, H, W, generator=g)
+    if poison:      # quotients outside the reciprocal division's range: the tile must be redone with IEEE division
+        flat = x.view(-1)
+        where = torch.randperm(flat.numel(), generator=g)[:64]
+        flat[where[:16]] = float("inf")
+        flat[where[16:32]] = -float("inf")
+        flat[where[32:48]] = 1e38                     # 1e38 / 0.2669 overflows
+        flat[where[48:]] = float("nan")
+    idx = torch.randint(0, 4, (R1, geo.lh * geo.lw), generator=g, dtype=torch.uint8)
+    if mode != "rrg-anypick":
+        idx[0] = 0                                   # the pipeline's k = 0 pick; "rrg-anypick": R1 = 1 with arbitrary picks
+    n = 2 * B * R1 + geo.nv * B
+    out = torch.randn(n, 4, nat, nat, generator=g).to(dtype)
+    out[2 * B * R1:][torch.rand(geo.nv * B, 4, nat, nat, generator=g) < 0.05] = 0
+    flags = (2 if mode.startswith("rrg") else 0) | (4 if dtype == torch.float16 else 0)
+    prm = dict(guidance=7.5, sqrt_beta_t=0.9637, sqrt_alpha_t=0.2669, sqrt_alpha_prev=0.3316, sqrt_dir=0.9434,
+               rrg_weight=731.25, rrg_norm=2.0 / (4 * H * W), flags=flags, n_renoise=0, R1=R1)
+    sp = native.StepParams(**prm)
+    for k in ("guidance", "sqrt_beta_t", "sqrt_alpha_t", "sqrt_alpha_prev", "sqrt_dir", "rrg_weight", "rrg_norm"):
+        prm[k] = float(getattr(sp, k))
+    owner = ws.owner_map(geo, R1, idx, "cpu").to(torch.uint8).contiguous().view(-1)
+    y, x0 = torch.full_like(x, float("nan")), torch.full_like(x, float("nan"))
+    info = (ctypes.c_int * 8)()
+    info[0] = grid_z
+    peers, bufs, per = None, [], 0
+    if world:
+        per = (n + world - 1) // world
+        for r in range(world):
+            buf = torch.full((per,) + tuple(out.shape[1:]), float("nan"), dtype=dtype)
+            lo, hi = min(r * per, n), min((r + 1) * per, n)
+            buf[:hi - lo] = out[lo:hi]
+            bufs.append(buf)
+        peers = (ctypes.c_void_p * world)(*[b.data_ptr() for b in bufs])
+    rc = emu.emu_wave_epilogue_half(ctypes.byref(plan), ctypes.byref(sp), R1, x.data_ptr(), None if world else out.data_ptr(),
+                                    peers, world or 0, per, native.dtype_code(dtype), idx.data_ptr(), owner.data_ptr(),
+                                    y.data_ptr(), x0.data_ptr() if x0_out else None, info)
+    assert rc == 0, rc
+    want, want_x0 = ws.spec_epilogue(geo, prm, x, out, idx, None)
+    bits = lambda t: t.view(torch.int32) if not poison else torch.where(torch.isnan(t), torch.zeros_like(t), t).view(torch.int32)
+    if x0_out:
+        assert torch.equal(bits(x0), bits(want_x0)), f"x0 max diff {(x0 - want_x0).abs().max().item():.3e} {list(info)}"
+        assert torch.equal(torch.isnan(x0), torch.isnan(want_x0))
+    assert torch.equal(bits(y), bits(want)), f"latent max diff {(y - want).abs().max().item():.3e} {list(info)}"
+    assert torch.equal(torch.isnan(y), torch.isnan(want))
+    return list(info)
+
+
+def test_half_epilogue_redoes_tiles_with_ieee_division_when_a_quotient_leaves_the_fast_range(emu):
+    for mode, dtype, R1 in (("plain", torch.bfloat16, 1), ("rrg", torch.float32, 1), ("rrg", torch.bfloat16, 3)):
+        run_half_case(emu, HALF_GEOS[1], mode, dtype, R1, poison=True)
+
+
+@pytest.mark.parametrize("cfg", HALF_GEOS)
+@pytest.mark.parametrize("mode,dtype,R1", [("plain", torch.bfloat16, 1), ("rrg", torch.bfloat16, 1), ("rrg", torch.float16, 1),
+                                           ("rrg-anypick", torch.float32, 1), ("plain", torch.float32, 3),
+                                           ("rrg", torch.bfloat16, 4), ("rrg", torch.float16, 2)])
+def test_half_epilogue_source_matches_spec_on_host(emu, cfg, mode, dtype, R1):
+    run_half_case(emu, cfg, mode, dtype, R1)
+
+
+def test_half_epilogue_peer_mapping_grid_stride_and_no_x0(emu):
+    run_half_case(emu, HALF_GEOS[0], "rrg", torch.bfloat16, 1, world=8)          # wave 2 of cfg3 over 8 ranks (2 idle)
+    run_half_case(emu, HALF_GEOS[1], "rrg", torch.float16, 3, world=3)
+    run_half_case(emu, HALF_GEOS[3], "plain", torch.float32, 2, world=2)
+    run_half_case(emu, HALF_GEOS[5], "rrg", torch.bfloat16, 2, grid_z=5)          # 12 (b, c) planes over a grid z of 5
+    run_half_case(emu, HALF_GEOS[1], "plain", torch.bfloat16, 1, x0_out=False)
+
+
+def test_half_flag_is_only_set_on_exact_half_tiling_geometries():
+    for cfg in GEOS:
+        B, H, W, nat, ds, window = cfg
+        geo = geometry.build_geometry(B, 4, H, W, nat, ds, window, window, nat - window)
+        exact = (2 * ds[0] == H and 2 * ds[1] == W and W % 8 == 0 and H % 2 == 0)
+        assert bool(geo.flags & native.PLAN_HALF_FAST) == exact, cfg

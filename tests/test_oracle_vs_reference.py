@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import components
+from conftest import components, oracle_models
 from oracle import reference_port as rp
 from oracle.ddim_restated import DDIMRestated
 from oracle.ref_shim import build_reference, reference_available, run_reference
@@ -129,3 +129,24 @@ def test_error_behaviour_matches_reference_on_the_host_side():
         bad._get_add_time_ids((4096, 8192), (0, 0), (4096, 8192), dtype=torch.float32)
     assert ed.get_downsample_size(1024, 2048) == o.get_downsample_size(1024, 2048)
     assert ed.get_downsample_size(1080, 1920) == o.get_downsample_size(1080, 1920)
+
+
+def test_sizes_not_divisible_by_8_are_floored():
+    """generate_image never raises on sizes that are not multiples of 8: ed:998 draws a (height // 8, width // 8) latent and
+    get_views only sees latent * 8 (ed:817, 827).  516 x 1028 runs like 512 x 1024 in the reference, in the oracle port and
+    in the product's wave-form host logic (no CUDA: spec kernels)."""
+    from conftest import make_ed
+    from oracle import wave_spec as ws
+    kw = dict(prompts="a cat", negative_prompts="blurry", guidance_scale=10.0, new_p=0.3, rrg_stop_t=0.2, rrg_init_weight=1000,
+              cosine_scale=10, repaint_sampling=True, num_inference_steps=2, resampling_steps=1)
+    o = _ref("2.1", 4)
+    o.seed_everything(0)
+    _, _, want = run_reference(o, progress=lambda it: it, height=516, width=1028, **kw)
+    assert want.shape == (1, 4, 64, 128)
+    m = oracle_models("2.1", 4)
+    rp.seed_all(0, "cpu")
+    assert torch.equal(rp.denoise(m, height=516, width=1028, **kw), want)
+    ed = make_ed("2.1", 4)
+    ed.seed_everything(0)
+    got = ws.denoise_wave_form(ed, height=516, width=1028, **kw)
+    assert (got - want).abs().max().item() <= 2e-5
