@@ -6,12 +6,29 @@
 
 namespace ed {
 
+// Where the decoded patches live.  Single GPU: one buffer.  Tiles sharded over ranks (ed_tile_blend_peer): patch p =
+// j*B + b lives in the buffer of rank p / per at local index p % per; `peers` is a device array of peer-mapped base
+// pointers and the centre crops are read straight from their owners over NVLink (no gathered copy).
+struct PatchSrc {
+  const void* local;
+  const void* const* peers;
+  int per;
+};
+
 // One thread produces VEC consecutive pixels of ROWS consecutive image rows of one (b, ch) plane.  ROWS rows aligned to
 // ROWS lie in the same latent row when scale % ROWS == 0, so the tile-cover lookups are shared and the ROWS patch
 // loads are independent (ROWS x VEC x sizeof(PT) bytes in flight per thread).
-template <typename PT, int VEC, int ROWS>
-__global__ void __launch_bounds__(256) tile_blend_kernel(const ed_tiles_t T, const PT* __restrict__ patches,
-                                                         float* __restrict__ image) {
+template <typename PT, int VEC, int ROWS, bool PEER>
+__global__ void __launch_bounds__(256) tile_blend_kernel(const ed_tiles_t T, const PatchSrc S, float* __restrict__ image) {
+  const long long patch_elems = (long long)T.CH * (T.core + 2 * T.pad) * T.scale * (T.core + 2 * T.pad) * T.scale;
+  auto patch = [&](int p) -> const PT* {           // start of decoded patch p = j*B + b (all CH channels)
+    if constexpr (PEER) {
+      const int r = p / S.per;
+      return static_cast<const PT*>(S.peers[r]) + (long long)(p - r * S.per) * patch_elems;
+    } else {
+      return static_cast<const PT*>(S.local) + (long long)p * patch_elems;
+    }
+  };
   const int Hp = T.H * T.scale, Wp = T.W * T.scale;
   const int side = (T.core + 2 * T.pad) * T.scale;   // decoded patch side in pixels
   const int padp = T.pad * T.scale;
@@ -67,7 +84,7 @@ __global__ void __launch_bounds__(256) tile_blend_kernel(const ed_tiles_t T, con
       // ---- fast path (one covering tile, the normal case): all ROWS row loads in flight, then clamp + store -------------
       const int j = r0 * T.ntc + c0;
       const int h0 = __ldg(T.tiles + j * 4 + 0), w0 = __ldg(T.tiles + j * 4 + 2);
-      const PT* src = patches + ((((long long)j * T.B + b) * T.CH + ch) * side + padp + (y0 - h0 * T.scale)) * side + padp +
+      const PT* src = patch(j * T.B + b) + ((long long)ch * side + padp + (y0 - h0 * T.scale)) * side + padp +
                       (xv * VEC - w0 * T.scale);
       float v[ROWS][VEC];
 #pragma unroll
@@ -95,7 +112,7 @@ __global__ void __launch_bounds__(256) tile_blend_kernel(const ed_tiles_t T, con
             const int py = padp + (y0 + r - h0 * T.scale);
             const int px = padp + (xv * VEC - w0 * T.scale);
             float v[VEC];
-            load_row(patches + ((((long long)j * T.B + b) * T.CH + ch) * side + py) * side + px, v);
+            load_row(patch(j * T.B + b) + ((long long)ch * side + py) * side + px, v);
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
               float p = __fadd_rn(__fmul_rn(v[e], 0.5f), 0.5f);
@@ -115,15 +132,17 @@ __global__ void __launch_bounds__(256) tile_blend_kernel(const ed_tiles_t T, con
 
 using namespace ed;
 
-extern "C" int ed_tile_blend(const ed_tiles_t* tiles, const void* patches, int patch_dtype, float* image,
-                             void* stream_) {
-  if (!tiles || !patches || !image) return ED_ERR_INVALID;
+static int launch_tile_blend(const ed_tiles_t* tiles, const void* patches, const void* const* peers, int world, int per,
+                             int patch_dtype, float* image, void* stream_) {
+  if (!tiles || (!patches && !peers) || !image) return ED_ERR_INVALID;
+  if (peers && (world <= 0 || per <= 0)) return ED_ERR_INVALID;
   const ed_tiles_t& T = *tiles;
   if (!T.tiles || !T.trow_first || !T.trow_cnt || !T.tcol_first || !T.tcol_cnt || T.ntiles <= 0 || T.ntc <= 0 ||
       T.scale <= 0 || T.B <= 0 || T.CH <= 0)
     return ED_ERR_INVALID;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int Wp = T.W * T.scale, Hp = T.H * T.scale;
+  // peer buffers are symmetric-memory allocations (>= 256-byte aligned); a patch is a multiple of 16 bytes when scale % 4 == 0
   const bool al = ((reinterpret_cast<uintptr_t>(image) & 15) == 0) && ((reinterpret_cast<uintptr_t>(patches) & 15) == 0);
   const int vec = (al && T.scale % 8 == 0) ? 8 : (al && T.scale % 4 == 0) ? 4 : 1;
   const int rows_per = (vec == 8) ? 8 : (T.scale % 4 == 0) ? 4 : 1;
@@ -131,11 +150,18 @@ extern "C" int ed_tile_blend(const ed_tiles_t* tiles, const void* patches, int p
   const dim3 block(32, 8);
   const int planes = T.B * T.CH;
   const dim3 g((cols + 31) / 32, (rows + 7) / 8, planes > 65535 ? 65535 : planes);
-#define ED_BLEND(PT)                                                                                          \
-  if (vec == 8 && rows_per == 8) tile_blend_kernel<PT, 8, 8><<<g, block, 0, stream>>>(T, (const PT*)patches, image); \
-  else if (vec == 4) tile_blend_kernel<PT, 4, 4><<<g, block, 0, stream>>>(T, (const PT*)patches, image);          \
-  else if (rows_per >= 4) tile_blend_kernel<PT, 1, 4><<<g, block, 0, stream>>>(T, (const PT*)patches, image);     \
-  else tile_blend_kernel<PT, 1, 1><<<g, block, 0, stream>>>(T, (const PT*)patches, image);
+  const PatchSrc S{patches, peers, per};
+#define ED_BLEND_AS(PT, PEER)                                                                         \
+  if (vec == 8 && rows_per == 8) tile_blend_kernel<PT, 8, 8, PEER><<<g, block, 0, stream>>>(T, S, image); \
+  else if (vec == 4) tile_blend_kernel<PT, 4, 4, PEER><<<g, block, 0, stream>>>(T, S, image);          \
+  else if (rows_per >= 4) tile_blend_kernel<PT, 1, 4, PEER><<<g, block, 0, stream>>>(T, S, image);     \
+  else tile_blend_kernel<PT, 1, 1, PEER><<<g, block, 0, stream>>>(T, S, image);
+#define ED_BLEND(PT)         \
+  if (peers) {               \
+    ED_BLEND_AS(PT, true)    \
+  } else {                   \
+    ED_BLEND_AS(PT, false)   \
+  }
   switch (patch_dtype) {
     case ED_F32: ED_BLEND(float) break;
     case ED_F16: ED_BLEND(__half) break;
@@ -143,6 +169,16 @@ extern "C" int ed_tile_blend(const ed_tiles_t* tiles, const void* patches, int p
     default: return ED_ERR_INVALID;
   }
 #undef ED_BLEND
+#undef ED_BLEND_AS
   ED_LAUNCH_CHECK();
   return ED_OK;
+}
+
+extern "C" int ed_tile_blend(const ed_tiles_t* tiles, const void* patches, int patch_dtype, float* image, void* stream_) {
+  return launch_tile_blend(tiles, patches, nullptr, 0, 0, patch_dtype, image, stream_);
+}
+
+extern "C" int ed_tile_blend_peer(const ed_tiles_t* tiles, const void* const* d_peer_patches, int world, int per,
+                                  int patch_dtype, float* image, void* stream_) {
+  return launch_tile_blend(tiles, nullptr, d_peer_patches, world, per, patch_dtype, image, stream_);
 }

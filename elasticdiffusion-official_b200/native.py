@@ -76,6 +76,7 @@ EXPORTS = {
     "ed_tile_gather": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                  C.c_int, C.c_void_p, C.c_void_p]),
     "ed_tile_blend": (C.c_int, [C.POINTER(Tiles), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "ed_tile_blend_peer": (C.c_int, [C.POINTER(Tiles), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -112,6 +112,14 @@ MODEL_KEYS = {"2.1": "stabilityai/stable-diffusion-2-1-base", "2.0": "stabilitya
               "XL1.0": "stabilityai/stable-diffusion-xl-base-1.0"}
 
 
+def shard_range(n, world, rank):
+    """(per, lo, hi): contiguous block partition of n units over `world` ranks - rank r owns [lo, hi) = [r*per, (r+1)*per)
+    clipped to n, per = ceil(n / world).  Used for the UNet samples of a wave and for the decode tiles; the peer kernels
+    resolve unit u to rank u // per."""
+    per = (n + world - 1) // world if world > 1 else n
+    return per, min(rank * per, n), min((rank + 1) * per, n)
+
+
 def _i32(dev, values):
     return torch.tensor(list(values) if len(values) else [0], dtype=torch.int32, device=dev)
 
@@ -356,6 +364,7 @@ class ElasticDiffusion(nn.Module):
         self.exchange = "p2p"         # multi-GPU exchange of UNet outputs: "p2p" = symmetric-memory buffers read by the fused
                                       # epilogue over NVLink (no collective), "nccl" = all_gather_into_tensor per wave
         self._sym = None
+        self._sym_decode = None
         self.unet_input_dtype = None  # dtype the gather kernels write the UNet batch in (None: fp32 like the reference)
         self.use_cuda_graphs = False  # capture each wave's UNet forward in a CUDA graph (static canvas / text buffers)
         self._graphs = {}
@@ -467,7 +476,10 @@ class ElasticDiffusion(nn.Module):
 
     def tiled_decode(self, latents, tile_batch=16):
         """ed:275-310 with the slicing / padding / blending done by ed_tile_gather (TMA, OOB zero fill) and
-        ed_tile_blend; the VAE decoder itself runs through PyTorch, `tile_batch` tiles per call."""
+        ed_tile_blend; the VAE decoder itself runs through PyTorch, `tile_batch` tiles per call.
+        With torch.distributed initialised (and `shard_waves`) the tiles are sharded over the ranks: rank r
+        decodes patches [r*per, (r+1)*per) into a symmetric-memory buffer and ed_tile_blend_peer reads the centre crops
+        straight from their owners over NVLink (exchange "p2p"), or the centre crops are all-gathered ("nccl")."""
         self._require_cuda()
         L = native.lib()
         latents = latents.float().contiguous()
@@ -477,27 +489,74 @@ class ElasticDiffusion(nn.Module):
         tabs = {k: _i32(dev, v) for k, v in tg.tables.items()}
         T = tg.core + 2 * tg.pad
         nt = len(tg.tiles)
-        boxes = torch.empty(nt * B, C, T, T, device=dev, dtype=torch.float32)
+        n = nt * B
+        grp, rank, ws = self._dist()
+        per, lo, hi = shard_range(n, ws, rank)
+        boxes = torch.empty(n, C, T, T, device=dev, dtype=torch.float32)
         native.check(L.ed_tile_gather(native.ptr(latents), B, C, H, W, native.ptr(tabs["tiles"]), nt, tg.core, tg.pad,
                                       native.ptr(boxes), native.stream_handle()), "ed_tile_gather")
         wdt = next(iter(self.vae.post_quant_conv.parameters())).dtype
         sf = self.vae_scale_factor
-        patches = None
-        for s in range(0, nt * B, tile_batch):
-            z = boxes[s:s + tile_batch].to(wdt) / self.vae.config.scaling_factor
-            dec = self.vae.decode(z).sample
-            if patches is None:
-                patches = torch.empty(nt * B, dec.shape[1], T * sf, T * sf, device=dev, dtype=dec.dtype)
-            patches[s:s + tile_batch] = dec
-        image = torch.empty(B, patches.shape[1], H * sf, W * sf, device=dev, dtype=torch.float32)
-        tt = native.Tiles(ntiles=nt, ntc=tg.ntc, core=tg.core, pad=tg.pad, scale=sf, B=B, CH=patches.shape[1], H=H, W=W,
-                          tiles=tabs["tiles"].data_ptr(), trow_first=tabs["trow_first"].data_ptr(),
-                          trow_cnt=tabs["trow_cnt"].data_ptr(), tcol_first=tabs["tcol_first"].data_ptr(),
-                          tcol_cnt=tabs["tcol_cnt"].data_ptr())
-        native.check(L.ed_tile_blend(ctypes.byref(tt), native.ptr(patches), native.dtype_code(patches.dtype),
-                                     native.ptr(image), native.stream_handle()), "ed_tile_blend")
+        cfg = self.vae.config
+        CH = int(cfg.get("out_channels", 3)) if hasattr(cfg, "get") else int(getattr(cfg, "out_channels", 3))
+        # the patches THIS rank decodes, (per, CH, T*sf, T*sf) in the decoder's dtype; sharded + p2p: a symmetric buffer
+        shape = (max(per, 1), CH, T * sf, T * sf)
+        sym = self._decode_symmetric(shape, wdt, grp) if (ws > 1 and self.exchange == "p2p") else None
+        patches = sym["buf"] if sym else torch.empty(shape, device=dev, dtype=wdt)
+        for s in range(lo, hi, tile_batch):
+            e = min(s + tile_batch, hi)
+            z = boxes[s:e].to(wdt) / self.vae.config.scaling_factor
+            patches[s - lo:e - lo] = self.vae.decode(z).sample
+        self.last_run["decode_tiles"] = self.last_run.get("decode_tiles", 0) + (hi - lo)
+        image = torch.empty(B, CH, H * sf, W * sf, device=dev, dtype=torch.float32)
+        mk = lambda pad: native.Tiles(ntiles=nt, ntc=tg.ntc, core=tg.core, pad=pad, scale=sf, B=B, CH=CH, H=H, W=W,
+                                      tiles=tabs["tiles"].data_ptr(), trow_first=tabs["trow_first"].data_ptr(),
+                                      trow_cnt=tabs["trow_cnt"].data_ptr(), tcol_first=tabs["tcol_first"].data_ptr(),
+                                      tcol_cnt=tabs["tcol_cnt"].data_ptr())
+        if ws == 1:
+            tt = mk(tg.pad)
+            native.check(L.ed_tile_blend(ctypes.byref(tt), native.ptr(patches), native.dtype_code(wdt),
+                                         native.ptr(image), native.stream_handle()), "ed_tile_blend")
+        elif sym:
+            tt = mk(tg.pad)
+            sym["hdl"].barrier(channel=0)                                  # every rank's patches are in its buffer
+            native.check(L.ed_tile_blend_peer(ctypes.byref(tt), native.ptr(sym["ptrs"]), ws, per, native.dtype_code(wdt),
+                                              native.ptr(image), native.stream_handle()), "ed_tile_blend_peer")
+            sym["hdl"].barrier(channel=0)                                  # nobody overwrites a buffer a peer still reads
+            self.last_run["peer_exchanges"] = self.last_run.get("peer_exchanges", 0) + 1
+        else:
+            # "nccl": all-gather of the centre crops (1/16 of the padded patches), then the same blend with pad = 0
+            import torch.distributed as dist
+            p0, c = tg.pad * sf, tg.core * sf
+            send = patches[:, :, p0:p0 + c, p0:p0 + c].contiguous()
+            crops = torch.empty(ws * per, CH, c, c, device=dev, dtype=wdt)
+            dist.all_gather_into_tensor(crops, send, group=grp)
+            self.last_run["collectives"] = self.last_run.get("collectives", 0) + 1
+            tt = mk(0)
+            native.check(L.ed_tile_blend(ctypes.byref(tt), native.ptr(crops), native.dtype_code(wdt), native.ptr(image),
+                                         native.stream_handle()), "ed_tile_blend")
         self.last_run["kernel_launches"] = self.last_run.get("kernel_launches", 0) + 2
         return image
+
+    def _decode_symmetric(self, shape, dtype, grp):
+        """Symmetric-memory buffer for this rank's decoded patches + the peer pointer table (cached per shape).
+        Falls back to the NCCL crop all-gather (with a note in last_run) when symmetric memory is unavailable."""
+        ent = self._sym_decode
+        if ent is not None and (ent["shape"], ent["dtype"]) == (shape, dtype):
+            return ent
+        try:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm
+            group = grp if grp is not None else dist.group.WORLD
+            buf = symm.empty(shape, dtype=dtype, device=self.device)
+            hdl = symm.rendezvous(buf, group)
+            ptrs = torch.tensor([int(p) for p in hdl.buffer_ptrs], dtype=torch.int64, device=self.device)
+            self._sym_decode = dict(buf=buf, hdl=hdl, ptrs=ptrs, shape=shape, dtype=dtype)
+        except Exception as e:  # pragma: no cover - depends on the box
+            self.last_run["exchange_fallback"] = f"symmetric memory unavailable ({type(e).__name__}: {e}); using nccl all_gather"
+            self.exchange = "nccl"
+            self._sym_decode = None
+        return self._sym_decode
 
     # -- the hot path ---------------------------------------------------------------------------------------------------
     def kernel_times_ms(self, reset=True):
@@ -549,11 +608,7 @@ class ElasticDiffusion(nn.Module):
         With torch.distributed initialised the samples are sharded over ranks and all-gathered (multi-GPU)."""
         grp, rank, ws = self._dist()
         n = canvas.shape[0]
-        if ws > 1:
-            per = (n + ws - 1) // ws
-            lo, hi = min(rank * per, n), min((rank + 1) * per, n)
-        else:
-            per, lo, hi = n, 0, n
+        per, lo, hi = shard_range(n, ws, rank)
         outs = []
         limit = self.unet_batch_limit or max(hi - lo, 1)
         for s in range(lo, hi, limit):

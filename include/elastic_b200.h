@@ -237,6 +237,14 @@ typedef struct {
  *   and clamp, ed:271, are fused here); image (B, CH, H*scale, W*scale) fp32. */
 int ed_tile_blend(const ed_tiles_t* tiles, const void* patches, int patch_dtype, float* image, void* stream);
 
+/* The same blend with the decode tiles sharded over `world` ranks ("tiled decode shards by tile"):
+ * rank r decoded patches [r*per, (r+1)*per) of the (j*B + b) order into its own buffer; `d_peer_patches` is a DEVICE array
+ * of `world` peer-mapped base pointers (symmetric memory) and every rank's kernel reads the centre crops it needs straight
+ * from their owners over NVLink - no gathered copy of the 16x larger padded patches, no collective.  The caller orders
+ * "all ranks finished decoding" before the launch (device-side symmetric-memory barrier). */
+int ed_tile_blend_peer(const ed_tiles_t* tiles, const void* const* d_peer_patches, int world, int per, int patch_dtype,
+                       float* image, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,6 +36,32 @@ for name, mode in [("xl_1024x2048_T3_R7", "p2p"), ("xl_1024x2048_T3_R7", "nccl")
         print(f"{name} [{mode}]: world={world} mse_vs_reference_golden={mse:.3e} identical_on_all_ranks={same} "
               f"nccl_collectives={ed.last_run['collectives']} p2p_exchanges={ed.last_run.get('peer_exchanges', 0)} "
               f"fallback={ed.last_run.get('exchange_fallback')} unet_samples_rank0={ed.last_run['unet_samples']}")
+# ---- tiled decode sharded by tile over the ranks: identical image on every rank, equal to the unsharded one ----
+g = load_golden("xl_2048x2048_T2_R2_tiled")
+z = g["latent"].to(f"cuda:{local}")
+for mode in ("p2p", "nccl"):
+    for low_vram_tiles in (False, True):       # True: stride core/2 -> up to 4 covering tiles per pixel (general blend path)
+        ed = make_ed(g["sd_version"], g["view_batch_size"], f"cuda:{local}")
+        ed.exchange = mode
+        ed.low_vram = low_vram_tiles
+        ed.last_run = {}
+        img = ed.tiled_decode(z, tile_batch=4)
+        tiles_here = ed.last_run["decode_tiles"]
+        ed.shard_waves = False
+        want = ed.tiled_decode(z, tile_batch=4)
+        ref0 = img.clone()
+        dist.broadcast(ref0, src=0)
+        # the VAE stub's convs see different batch compositions per rank: bit-equality is not guaranteed, 1e-5 is
+        err = (img - want).abs().max().item()
+        same = torch.equal(ref0, img)
+        total = torch.tensor([tiles_here], device=f"cuda:{local}")
+        dist.all_reduce(total)
+        good = err <= 1e-5 and same and int(total.item()) == (64 if not low_vram_tiles else 225)
+        ok &= good
+        if rank == 0:
+            print(f"tiled_decode [{mode}, stride {'core/2' if low_vram_tiles else 'core'}]: world={world} tiles_rank0={tiles_here} "
+                  f"tiles_total={int(total.item())} max_abs_vs_unsharded={err:.3e} identical_on_all_ranks={same} "
+                  f"fallback={ed.last_run.get('exchange_fallback')} -> {'ok' if good else 'FAILED'}")
 flag = torch.tensor([int(ok)], device=f"cuda:{local}")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:

@@ -5,6 +5,8 @@ mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
 STAGES=${@:-"kernels e2e bench"}
 CASES='ed_wave_epilogue+renoise,ed_wave_epilogue+rrg(wave2:R1=1),ed_wave_epilogue(wave2:R1=1),ed_wave_epilogue+rrg'
+# the snapshot may carry a library older than the sources (edits while the call was queued): rebuild first (seconds)
+python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1 || { echo "[build] FAILED"; tail -20 gpurun_out/build.log; }
 for s in $STAGES; do
   t0=$(date +%s)
   case $s in
@@ -21,6 +23,10 @@ for s in $STAGES; do
     probe) timeout 600 python scripts/probe_unet.py gpurun_out/probe_unet.json > gpurun_out/probe_unet.log 2>&1; rc=$? ;;
     launches) BENCH_GRAPHS=0 BENCH_CUPROF=1 timeout 420 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 5000 --csv \
            --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-extras --no-parity > gpurun_out/launches.log 2>&1; rc=$? ;;
+    multi) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29533 \
+           scripts/check_multi_gpu.py > gpurun_out/multi_gpu_n${NGPU:-2}.log 2>&1; rc=$? ;;
+    scale) for n in ${SCALE_NS:-"2 4 8"}; do timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 \
+             --master-port 29544 bench.py --gpus $n --steps 8 --warmup 3 --no-extras > gpurun_out/bench_n$n.json 2> gpurun_out/bench_n$n.err; done; rc=$? ;;
     smoke) timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; rc=$? ;;
     *) echo "unknown stage $s"; rc=99 ;;
   esac

@@ -345,7 +345,36 @@ def test_tile_gather_and_blend_match_spec(B, H, W, sample, low_vram):
                       tcol_cnt=tabs["tcol_cnt"].data_ptr())
     native.check(L.ed_tile_blend(ctypes.byref(tt), native.ptr(patches), native.ED_F32, native.ptr(image), st))
     torch.cuda.synchronize()
-    assert torch.equal(image, ws.spec_tile_blend(patches, tg.tiles, B, H, W, tg.core, tg.pad, scale))
+    want = ws.spec_tile_blend(patches, tg.tiles, B, H, W, tg.core, tg.pad, scale)
+    assert torch.equal(image, want)
+    # tiles sharded over ranks, exercised on one GPU: ed_tile_blend_peer with the pointer table pointing at separate local
+    # buffers (patch p lives in buffer p // per), ragged last rank and idle ranks; for every dtype of decoded patches
+    for world, dt in ((2, torch.float32), (3, torch.bfloat16), (8, torch.float16)):
+        pd = patches.to(dt)
+        n = nt * B
+        per = (n + world - 1) // world
+        bufs = []
+        for r in range(world):
+            buf = torch.full((per,) + tuple(pd.shape[1:]), float("nan"), device=DEV, dtype=dt)
+            lo, hi = min(r * per, n), min((r + 1) * per, n)
+            buf[:hi - lo] = pd[lo:hi]
+            bufs.append(buf)
+        ptrs = torch.tensor([b_.data_ptr() for b_ in bufs], dtype=torch.int64, device=DEV)
+        img2 = torch.full_like(image, float("nan"))
+        native.check(L.ed_tile_blend_peer(ctypes.byref(tt), native.ptr(ptrs), world, per, native.dtype_code(dt), native.ptr(img2), st))
+        torch.cuda.synchronize()
+        assert torch.equal(img2, ws.spec_tile_blend(pd, tg.tiles, B, H, W, tg.core, tg.pad, scale)), (world, dt)
+    # the "nccl" exchange of the sharded decode all-gathers centre crops and blends with pad = 0: same image
+    p0, c = tg.pad * scale, tg.core * scale
+    crops = patches[:, :, p0:p0 + c, p0:p0 + c].contiguous()
+    tt0 = native.Tiles(ntiles=nt, ntc=tg.ntc, core=tg.core, pad=0, scale=scale, B=B, CH=3, H=H, W=W,
+                       tiles=tabs["tiles"].data_ptr(), trow_first=tabs["trow_first"].data_ptr(),
+                       trow_cnt=tabs["trow_cnt"].data_ptr(), tcol_first=tabs["tcol_first"].data_ptr(),
+                       tcol_cnt=tabs["tcol_cnt"].data_ptr())
+    img3 = torch.full_like(image, float("nan"))
+    native.check(L.ed_tile_blend(ctypes.byref(tt0), native.ptr(crops), native.ED_F32, native.ptr(img3), st))
+    torch.cuda.synchronize()
+    assert torch.equal(img3, want)
 
 
 def test_view_gather_roundtrip_at_l2_exceeding_size():
