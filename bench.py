@@ -38,8 +38,21 @@ WORKLOADS = {
     "cfg3": ("XL1.0", "XL1.0", 1024, 2048, 16, 50, 7, 2048, 1280),
     "cfg4": ("XL1.0", "XL1.0", 2048, 2048, 16, 50, 7, 2048, 1280),
     "cfg2": ("2.1", "2.1", 512, 1024, 8, 50, 4, 1024, None),
+    # cfg5 = cfg3 + ControlNet (the twin elastic_diffusion_w_controlnet.py): a ControlNet forward precedes every UNet forward
+    "cfg5": ("XL1.0", "XL1.0", 1024, 2048, 16, 50, 7, 2048, 1280),
     "tiny": ("XL1.0", "tiny-xl", 1024, 2048, 16, 50, 7, 64, 32),     # quick functional run of the same topology
+    "tiny5": ("XL1.0", "tiny-xl", 1024, 2048, 16, 50, 7, 64, 32),    # ... with the ControlNet twin
 }
+CONTROLNET = {"cfg5", "tiny5"}
+COND_SCALE = 0.8
+
+
+def condition_image(workload, device="cpu"):
+    """cfg5's condition: a fixed-seed uniform [0, 1] image of the prepared size (1, 3, ds_h*8, ds_w*8)."""
+    sd, preset, H, W = WORKLOADS[workload][:4]
+    f = max(max(H, W) / (1024 if "XL" in sd else 512), 1)
+    ds = (int((H // f) // 8), int((W // f) // 8))
+    return torch.rand(1, 3, ds[0] * 8, ds[1] * 8, generator=torch.Generator().manual_seed(7)).to(device)
 GEN = dict(prompts="a photo of a mountain lake at sunrise", negative_prompts="blurry, ugly", guidance_scale=10.0,
            new_p=0.3, rrg_stop_t=0.2, rrg_init_weight=1000, cosine_scale=10.0, repaint_sampling=True)
 
@@ -49,14 +62,17 @@ def pkg():
 
 
 def build_modules(workload, device, unet_dtype):
+    """(unet, vae, text encoder, controlnet or None): the stand-ins of the workload on `device`."""
     sd, preset, H, W, vb, T, R, cross, pooled = WORKLOADS[workload]
     import standins as syn
     unet = syn.StandInUNet(preset, device=device, dtype=unet_dtype).eval()
-    for p in unet.parameters():
-        p.requires_grad_(False)
+    cn = syn.StandInControlNet(preset, device=device, dtype=unet_dtype, seed=11).eval() if workload in CONTROLNET else None
+    for m in (unet, cn):
+        for p in (m.parameters() if m is not None else ()):
+            p.requires_grad_(False)
     vae = syn.StubVAE().to(device)
     txt = syn.StubTextEncoder(cross, pooled, device=device)
-    return unet, vae, txt
+    return unet, vae, txt, cn
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -305,7 +321,7 @@ def host_threads():
     return torch.get_num_threads()
 
 
-def run_reference_loop(workload, device, unet, n_warm, n_steps, kind=None):
+def run_reference_loop(workload, device, unet, n_warm, n_steps, kind=None, controlnet=None):
     """The reference's own `generate_image` loop (ed:1013-1078) for n_warm + n_steps denoise steps on `device`, timed
     per step (CUDA events on cuda, perf_counter on cpu) through the `progress` iterator the loop is driven by.
     Returns (seconds for n_steps, kind, latent after the last timed step or None)."""
@@ -320,6 +336,8 @@ def run_reference_loop(workload, device, unet, n_warm, n_steps, kind=None):
     vae = syn.StubVAE().to(device)
     txt = syn.StubTextEncoder(cross, pooled, device=device)
     kw = dict(GEN, height=H, width=W, num_inference_steps=T, resampling_steps=R)
+    if controlnet is not None:          # the ControlNet twin (elastic_diffusion_w_controlnet.py)
+        kw.update(condition_image=condition_image(workload, device), controlnet_conditioning_scale=COND_SCALE)
     marks = []
 
     def mark():
@@ -333,7 +351,7 @@ def run_reference_loop(workload, device, unet, n_warm, n_steps, kind=None):
     with torch.no_grad():
         if kind == "reference":
             o = ref_shim.build_reference(unet, vae, DDIMRestated(), txt, sd_version=sd, device=device, view_batch_size=vb,
-                                         projection_dim=pooled)
+                                         projection_dim=pooled, controlnet=controlnet)
             o.seed_everything(0)
 
             def progress(it):                      # the reference iterates `progress(self.scheduler.timesteps)` (ed:1013)
@@ -347,7 +365,7 @@ def run_reference_loop(workload, device, unet, n_warm, n_steps, kind=None):
             except _Stop:
                 pass
         else:
-            m = rp.Models(unet, vae, DDIMRestated(), txt, sd, device, vb, projection_dim=pooled)
+            m = rp.Models(unet, vae, DDIMRestated(), txt, sd, device, vb, projection_dim=pooled, controlnet=controlnet)
             rp.seed_all(0, device)
             mark()
 
@@ -387,7 +405,12 @@ def cpu_unet_forward_s(unet, workload, reps=1):
     return best
 
 
-N_SAMPLES = {"cfg3": 26, "cfg5": 26, "cfg2": 20, "cfg4": 50, "tiny": 26}   # UNet sample-forwards per repaint step
+N_SAMPLES = {"cfg3": 26, "cfg5": 26, "cfg2": 20, "cfg4": 50, "tiny": 26, "tiny5": 26}   # UNet sample-forwards per repaint step
+
+
+def cpu_controlnet(workload):
+    import standins as syn
+    return syn.StandInControlNet(WORKLOADS[workload][1], seed=11).eval() if workload in CONTROLNET else None
 
 
 def cpu_reference_measured(workload, n_steps=1):
@@ -400,7 +423,7 @@ def cpu_reference_measured(workload, n_steps=1):
     cores = host_threads()
     unet = syn.StandInUNet(preset).eval()
     t_b2 = cpu_unet_forward_s(unet, workload)
-    sec, kind = run_reference_loop(workload, "cpu", unet, 0, n_steps)
+    sec, kind = run_reference_loop(workload, "cpu", unet, 0, n_steps, controlnet=cpu_controlnet(workload))
     step_s = sec / n_steps
     return {"value": 1.0 / step_s, "unit": "denoise-steps/s", "cores": cores, "kind": kind, "steps_timed": n_steps,
             "sample": f"{n_steps} full denoise step(s) of the {'unmodified reference (baseline/_ref via oracle/ref_shim)' if kind == 'reference' else 'oracle port'} "
@@ -419,10 +442,14 @@ def cpu_reference_sample(workload):
     cores = host_threads()
     xl = sd.startswith("XL")
     stub = syn.StubUNet(sample_size=128 if xl else 64, cross_dim=cross, xl=xl, pooled_dim=pooled or 8)
-    glue, kind = run_reference_loop(workload, "cpu", stub, 1, 1)
+    glue, kind = run_reference_loop(workload, "cpu", stub, 1, 1,
+                                    controlnet=syn.StubControlNet(cross_dim=cross) if workload in CONTROLNET else None)
     unet = syn.StandInUNet(preset).eval()
     cpu_unet_forward_s(unet, workload)                    # warm-up
     t_b2 = cpu_unet_forward_s(unet, workload)
+    if workload in CONTROLNET:     # + the ControlNet forward that precedes every UNet forward: the UNet's encoder half, timed
+        cn = cpu_controlnet(workload)                    # as its share of the UNet's FLOPs (measured on the GPU: ~0.45)
+        t_b2 *= 1.0 + sum(p.numel() for p in cn.parameters()) / sum(p.numel() for p in unet.parameters())
     n_samples = N_SAMPLES[workload]
     step_s = (n_samples / 2) * t_b2 + glue
     return {"value": 1.0 / step_s, "unit": "denoise-steps/s", "cores": cores, "kind": kind, "steps_timed": 0,
@@ -432,10 +459,11 @@ def cpu_reference_sample(workload):
                       f"printed by `bench.py --impl reference`", "t_unet_b2_s": t_b2, "glue_s": glue}
 
 
-def reference_gpu_eager_same_dtype(workload, device, unet_bf16, steps=2, warm=1):
+def reference_gpu_eager_same_dtype(workload, device, unet_bf16, steps=2, warm=1, controlnet=None):
     """The reference loop, eager, with the SAME bf16 / no-autocast UNet object this bench's own arm uses: value / this
     isolates the pipeline speed-up (wave batching, CUDA graphs, fused kernels) from the dtype / autocast change."""
-    sec, kind = run_reference_loop(workload, device, _NoAutocast(unet_bf16), warm, steps)
+    sec, kind = run_reference_loop(workload, device, _NoAutocast(unet_bf16), warm, steps,
+                                   controlnet=_NoAutocast(controlnet) if controlnet is not None else None)
     return {"value": steps / sec, "unit": "denoise-steps/s", "ms_per_step": 1e3 * sec / steps, "steps": steps, "kind": kind,
             "note": "reference loop, eager, with this bench's bf16 UNet (autocast switched off inside the forward)"}
 
@@ -448,10 +476,12 @@ def reference_gpu_eager_stock(workload, device, steps=2, warm=1):
     import standins as syn
     sd, preset = WORKLOADS[workload][:2]
     unet = syn.StandInUNet(preset, device=device, dtype=torch.float32).eval()
-    for p in unet.parameters():
-        p.requires_grad_(False)
-    sec, kind = run_reference_loop(workload, device, unet, warm, steps)
-    del unet
+    cn = syn.StandInControlNet(preset, device=device, dtype=torch.float32, seed=11).eval() if workload in CONTROLNET else None
+    for m in (unet, cn):
+        for p in (m.parameters() if m is not None else ()):
+            p.requires_grad_(False)
+    sec, kind = run_reference_loop(workload, device, unet, warm, steps, controlnet=cn)
+    del unet, cn
     torch.cuda.empty_cache()
     return {"value": steps / sec, "unit": "denoise-steps/s", "ms_per_step": 1e3 * sec / steps, "steps": steps, "kind": kind,
             "note": ("unmodified reference (baseline/_ref)" if kind == "reference" else "oracle port (restated reference)") +
@@ -478,7 +508,7 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
-def parity_check(ed, unet, workload, device, world, rank, kw, n_steps=2):
+def parity_check(ed, unet, workload, device, world, rank, kw, n_steps=2, controlnet=None):
     """Parity of the EXACT configuration that was just timed (bf16 stand-in UNet, autocast off, CUDA graphs, device Philox
     RNG, at N > 1 the p2p exchange): `n_steps` un-timed denoise steps from seed 0 against the oracle port run eagerly on the
     same device with the same UNet object (per-pass batch-2 / batch-nv calls), plus, at N > 1, bit-equality of the latent
@@ -507,7 +537,8 @@ def parity_check(ed, unet, workload, device, world, rank, kw, n_steps=2):
                 got["x"] = x.clone()
                 raise _Stop
         m = rp.Models(_NoAutocast(unet), syn.StubVAE().to(device), DDIMRestated(),
-                      syn.StubTextEncoder(cross, pooled, device=device), sd, device, vb, projection_dim=pooled)
+                      syn.StubTextEncoder(cross, pooled, device=device), sd, device, vb, projection_dim=pooled,
+                      controlnet=_NoAutocast(controlnet) if controlnet is not None else None)
         rp.seed_all(0, device)
         try:
             rp.denoise(m, step_callback=cb, **{k: v for k, v in kw.items() if k != "progress"})
@@ -522,10 +553,60 @@ def parity_check(ed, unet, workload, device, world, rank, kw, n_steps=2):
     return out
 
 
+def decode_timing(ed, workload, device, world, rank):
+    """cfg4 (tiled_decoder=True): the tiled VAE decode of the final latent (ed:275-310) - 64 tiles of 1024^2 px at SDXL
+    2048x2048 - with an SDXL-VAE-shaped fp32 decoder stand-in, tiles sharded over the ranks, centre crops blended by
+    ed_tile_blend[_peer].  Not part of the steps/s metric; reported beside it (+ the unmodified reference's own
+    tiled_decode, eager, on the same GPU at N = 1)."""
+    import torch.distributed as dist
+    import standins as syn
+    sd, preset, H, W = WORKLOADS[workload][:4]
+    vae = syn.StandInVAE(device=device).eval()
+    for p in vae.parameters():
+        p.requires_grad_(False)
+    old_vae, ed.vae = ed.vae, vae
+    z = torch.randn(1, 4, H // 8, W // 8, device=device, generator=torch.Generator(device=device).manual_seed(3))
+    out = {}
+    try:
+        with torch.no_grad():
+            img = ed.tiled_decode(z, tile_batch=8)                         # warm-up (cuDNN plans, symmetric buffers)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            img = ed.tiled_decode(z, tile_batch=8)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            out = {"ms": float(ms.item()), "image": list(img.shape), "tiles_this_rank": ed.last_run.get("decode_tiles", 0) // 2,
+                   "sharded_over": world, "exchange": ed.exchange if world > 1 else None,
+                   "vae": "StandInVAE (SDXL-VAE-shaped decoder, 49.5 M parameters, fp32, random weights)"}
+            if world == 1:
+                from oracle import ref_shim
+                from oracle.ddim_restated import DDIMRestated
+                if ref_shim.reference_available():
+                    o = ref_shim.build_reference(ed.unet, vae, DDIMRestated(), None, sd_version=sd, device=device)
+                    want = o.tiled_decode(z)                                # warm-up + parity of the image
+                    torch.cuda.synchronize()
+                    e0.record()
+                    o.tiled_decode(z)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    out["reference_gpu_eager_ms"] = e0.elapsed_time(e1)
+                    out["max_abs_vs_reference"] = float((img - want).abs().max().item())
+    finally:
+        ed.vae = old_vae
+    return out
+
+
 def workload_config(workload, n):
     sd, preset, H, W, vb, T, R, cross, pooled = WORKLOADS[workload]
     return {"workload": f"{workload}: SD{sd} {H}x{W} view_batch_size={vb} steps={T} resampling_steps={R} rrg=1000 "
-                        "cosine_scale=10 repaint", "unet": f"StandInUNet({preset}) random weights",
+                        "cosine_scale=10 repaint" + (" + ControlNet twin, conditioning_scale=0.8" if workload in CONTROLNET else ""),
+            "unet": f"StandInUNet({preset}) random weights" + (f" + StandInControlNet({preset})" if workload in CONTROLNET else ""),
             "parallelism": f"wave-sample sharding x{n}" if n > 1 else "single GPU",
             "timing": "CUDA events; latent working set < L2, UNet activations/weights (5 GB bf16) >> L2"}
 
@@ -539,6 +620,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=list(WORKLOADS))
     ap.add_argument("--no-extras", action="store_true", help="skip roofline / cpu_baseline / e2e legs (debug)")
+    ap.add_argument("--no-decode", action="store_true", help="cfg4: skip the tiled-decode timing")
     ap.add_argument("--no-parity", action="store_true", help="skip the un-timed parity steps against the oracle port (debug)")
     ap.add_argument("--roofline-only", action="store_true", help="only the L2-exceeding kernel roofline table (debug / ncu)")
     ap.add_argument("--roofline-cases", default="", help="comma-separated kernel_rooflines case names (with --roofline-only)")
@@ -566,9 +648,10 @@ def main():
     sd, preset, H, Wd, vb, T, R, cross, pooled = WORKLOADS[args.workload]
     P = pkg()
     unet_dtype = torch.bfloat16
-    unet, vae, txt = build_modules(args.workload, device, unet_dtype)
-    ed = P.ElasticDiffusion.from_components(device, unet, vae, None, txt, sd_version=sd, view_batch_size=vb,
-                                            projection_dim=pooled)
+    unet, vae, txt, cn = build_modules(args.workload, device, unet_dtype)
+    cls = P.controlnet.ElasticDiffusion if cn is not None else P.ElasticDiffusion       # cfg5: the ControlNet twin
+    ed = cls.from_components(device, unet, vae, None, txt, sd_version=sd, view_batch_size=vb, projection_dim=pooled,
+                             controlnet=cn)
     ed.autocast = False                 # UNet weights are bf16 already: no per-call weight re-casting
     # UNet batch stays fp32 (like the reference's latents): the view gather then runs on its TMA path (UTMALDG/UTMASTG)
     # in the pipeline too; the stand-in casts to bf16 in its first op (one 5 MB elementwise pass per wave)
@@ -578,6 +661,8 @@ def main():
     if os.environ.get("BENCH_CL", "0") == "1":
         unet.to(memory_format=torch.channels_last)
     kw = dict(GEN, height=H, width=Wd, num_inference_steps=T, resampling_steps=R, progress=lambda it: it)
+    if cn is not None:
+        kw.update(condition_image=condition_image(args.workload, device), controlnet_conditioning_scale=COND_SCALE)
 
     def barrier():
         if world > 1:
@@ -645,6 +730,9 @@ def main():
             "unet": {"calls": ed.last_run["unet_calls"], "samples": ed.last_run["unet_samples"],
                      "collectives": ed.last_run["collectives"], "p2p_exchanges": ed.last_run.get("peer_exchanges", 0),
                      "exchange": ed.exchange, "exchange_fallback": ed.last_run.get("exchange_fallback")},
+            # host side: the look-ahead RNG planner (runs under the previous step's GPU work) and the background strips
+            "host": {"plan_ms_per_step": round(ed.last_run.get("plan_host_ms", 0.0) / max(ed.last_run["steps"], 1), 3),
+                     "strips": ed.last_run.get("vae_encodes", 0), "vae_encode_calls": ed.last_run.get("vae_encode_calls", 0)},
             "kernels_in_step": {k: {"launches": n, "avg_us": round(1e3 * ms / max(n, 1), 2)} for k, (n, ms) in ktimes.items()},
             # which wave-epilogue kernel AUTO took during this run (warm-up included): launches without a noise stream ->
             # the half kernels (exact 1/2 ratio); re-noise launches: one latent per launch is small and L2-resident -> the
@@ -671,16 +759,20 @@ def main():
                                          "L2-resident and latency-bound, see kernels_in_step"}
             line["roofline_all"] = roof
     if not args.no_parity:
-        par = parity_check(ed, unet, args.workload, device, world, rank, kw)
+        par = parity_check(ed, unet, args.workload, device, world, rank, kw, controlnet=cn)
         if rank == 0:
             line["parity"] = par
+    if args.workload == "cfg4" and not args.no_decode:
+        dec = decode_timing(ed, args.workload, device, world, rank)
+        if rank == 0:
+            line["decode"] = dec
     if not args.no_extras and rank == 0 and world == 1:
         ed._graphs = {}
         torch.cuda.empty_cache()
         try:   # GPU-vs-GPU: the reference's own eager path on this B200 (the 10x target's denominator), two dtypes
-            same = reference_gpu_eager_same_dtype(args.workload, device, unet)
-            del unet
-            ed.unet = None
+            same = reference_gpu_eager_same_dtype(args.workload, device, unet, controlnet=cn)
+            del unet, cn
+            ed.unet = ed.controlnet = None
             torch.cuda.empty_cache()
             stock = reference_gpu_eager_stock(args.workload, device)
             line["reference_gpu_eager"] = stock

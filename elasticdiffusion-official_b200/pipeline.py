@@ -196,6 +196,7 @@ class RngLedger:
                     o.upcast_vae()
                     img = img.float()
                 dist = o.vae.encode(img.to(o.vae.dtype) if not upcast else img).latent_dist
+                o.last_run["vae_encode_calls"] = o.last_run.get("vae_encode_calls", 0) + 1
                 if self.rng_dev == self.dev:
                     z = dist.sample()
                 else:   # test mode (CPU generator): same formula as DiagonalGaussianDistribution.sample
@@ -214,6 +215,81 @@ class RngLedger:
         # every non-empty use consumes one numpy draw and re-keys torch, hit or miss (ed:359)
         self._seed(int(np.random.randint(100000)))
         return hit
+
+    def _strip_keys(self, inner_h, inner_w, t):
+        """(key, h, w) of the non-empty strips of one padded unet_step, in the order pad_events touches them."""
+        nat = self.geo.native
+        l, r = pad_split(nat, inner_w)
+        tp, b = pad_split(nat, inner_h)
+        wide = inner_w + l + r
+        cand = [("3_1", inner_h, l), ("3_2", inner_h, r), ("2_1", tp, wide), ("2_2", b, wide)]
+        return [(f"{tag}_{h}_{w}_{t}", h, w) for tag, h, w in cand if h > 0 and w > 0]
+
+    def precompute_strips(self, ts, chunk=32):
+        """SURVEY 8 row f2 (the reference's TODO ed:340): every background strip of the run - a pure function of its id
+        string (dim, side, h, w, t) - built BEFORE the loop with batched VAE encodes instead of one fp32 encode per cache
+        miss inside the look-ahead planner.  Per strip the generator operations are exactly those of ed:335-358 (re-key
+        from the md5 of the id, rand(1,3) colour, the latent distribution's randn, add_noise's randn) in the same order on
+        a re-keyed generator; only the VAE encode between the colour draw and the sample draw - which consumes no random
+        numbers - is deferred and batched.  The global generators are restored afterwards, so the loop's own draws
+        (ed:502-544, 701) and the per-use numpy re-seeds (ed:359) are untouched: RNG-neutral.  Returns the number of
+        batched VAE encode calls."""
+        o, g = self.o, self.geo
+        todo, seen = [], set()
+        for t in ts:
+            shapes = [(g.lh, g.lw)] + ([(g.vh, g.vw)] if (g.vh < g.native or g.vw < g.native) else [])
+            for ih, iw in shapes:
+                for key, h, w in self._strip_keys(ih, iw, t):
+                    if key not in seen and key not in self.strip_cache:
+                        seen.add(key)
+                        todo.append((key, h, w, t))
+        if not todo:
+            return 0
+        cpu_state = torch.default_generator.get_state()
+        cuda_gen = None
+        if self.dev.type == "cuda":
+            idx = self.dev.index if self.dev.index is not None else torch.cuda.current_device()
+            cuda_gen = torch.cuda.default_generators[idx]
+            cuda_state = cuda_gen.get_state()
+        calls = 0
+        try:
+            with torch.autocast("cuda", enabled=False):
+                upcast = o.vae.dtype == torch.float16 and o.vae.config.force_upcast
+                if o.low_vram:
+                    o.vae.to(self.dev)
+                if upcast:
+                    o.upcast_vae()
+                vdt = torch.float32 if upcast else o.vae.dtype
+                C = g.C
+                draws = {}
+                for key, h, w, t in todo:                                   # generator operations, in the reference's order
+                    self._seed(self._md5_seed(key))                         # ed:335
+                    colour = torch.rand(1, 3, device=self.rng_dev).to(self.dev)              # ed:336
+                    eps_sample = self._randn((1, C, h, w), vdt)             # latent_dist.sample() (ed:350)
+                    eps_noise = self._randn((1, C, h, w), vdt)              # randn_like (ed:356)
+                    draws[key] = (colour, eps_sample, eps_noise)
+                by_shape = {}
+                for item in todo:
+                    by_shape.setdefault((item[1], item[2]), []).append(item)
+                sf = o.vae_scale_factor
+                for (h, w), items in by_shape.items():
+                    for s in range(0, len(items), chunk):
+                        part = items[s:s + chunk]
+                        imgs = torch.cat([draws[k][0] for k, *_ in part])[:, :, None, None].expand(-1, -1, h * sf, w * sf)
+                        dist = o.vae.encode(imgs.to(vdt).contiguous()).latent_dist              # ONE encode for the chunk
+                        calls += 1
+                        for j, (key, _, _, t) in enumerate(part):
+                            _, e1, e2 = draws[key]
+                            z = (dist.mean[j:j + 1] + dist.std[j:j + 1] * e1) * o.vae.config.scaling_factor
+                            ac = o.scheduler.alphas_cumprod[int(t)]
+                            self.strip_cache[key] = (float(ac ** 0.5) * z + float((1 - ac) ** 0.5) * e2).float().contiguous()
+                if upcast:
+                    o.vae.to(dtype=torch.float16)
+        finally:
+            torch.default_generator.set_state(cpu_state)
+            if cuda_gen is not None:
+                cuda_gen.set_state(cuda_state)
+        return calls
 
     def pad_events(self, inner_h, inner_w, t):
         """Background strips of one padded `unet_step` (ed:405-408, 372-389): width strips first (dim 3), then height
@@ -366,6 +442,7 @@ class ElasticDiffusion(nn.Module):
         self._sym = None
         self._sym_decode = None
         self.unet_input_dtype = None  # dtype the gather kernels write the UNet batch in (None: fp32 like the reference)
+        self.precompute_strips = True  # background strips of all timesteps built before the loop in batched VAE encodes
         self.use_cuda_graphs = False  # capture each wave's UNet forward in a CUDA graph (static canvas / text buffers)
         self._graphs = {}
         self.profile_kernels = False  # record CUDA-event pairs around every libelastic_b200 launch (bench.py)
@@ -775,6 +852,9 @@ class ElasticDiffusion(nn.Module):
             self.vae.cpu()
             self.unet.to(dev)
 
+        # all background strips of the run, batched, before the loop (row f2); RNG-neutral
+        n_steps = len(ts) if max_steps is None else min(len(ts), max_steps)
+        self.last_run["vae_encode_calls"] = ledger.precompute_strips(ts[:n_steps]) if self.precompute_strips else 0
         R = resampling_steps
         n_re = self.scheduler.config.num_train_timesteps // T
         if n_re > native.ED_MAX_RENOISE:
@@ -881,6 +961,7 @@ class ElasticDiffusion(nn.Module):
         def plan_step(i):
             """All RNG of step i in the reference's order; touches no UNet output, so it is
             issued one step AHEAD and overlaps with the GPU work of step i-1."""
+            t_host = time.perf_counter()
             t = ts[i]
             last = i == len(ts) - 1
             repaint = bool(repaint_sampling and R > 0 and not last)                            # ed:1038
@@ -897,9 +978,9 @@ class ElasticDiffusion(nn.Module):
                 _, p["strips_g2"] = ledger.global_pass(t, 0, 1 - new_p)                         # ed:1043
                 p["strips_v2"] = ledger.local_pass(t, self.view_batch_size)                     # ed:1049
                 p["renoise"] = renoise_scalars(self.scheduler, ts[i + 1])
+            self.last_run["plan_host_ms"] = self.last_run.get("plan_host_ms", 0.0) + 1e3 * (time.perf_counter() - t_host)
             return p
 
-        n_steps = len(ts) if max_steps is None else min(len(ts), max_steps)
         # NOTE on buffer reuse: `noise` and `idx1` are single device buffers; the draws / copies of step i+1 are
         # enqueued on the main stream AFTER the kernels of step i, so stream order protects them.
         nxt = None

@@ -239,6 +239,9 @@ def denoise_wave_form(ed, prompts, negative_prompts="", height=768, width=768, n
     x = ledger.initial_latent((B, C, H, W), ed.torch_dtype)
     ed.scheduler.set_timesteps(T)
     ts = ed.scheduler.timesteps
+    if getattr(ed, "precompute_strips", False):     # product behaviour: all background strips before the loop, batched
+        ed.last_run = dict(getattr(ed, "last_run", {}) or {})
+        ed.last_run["vae_encode_calls"] = ledger.precompute_strips(ts)
     R, nv = resampling_steps, geo.nv
     n_re = ed.scheduler.config.num_train_timesteps // T
     text_pair, pool_pair = torch.cat([un_text, co_text]), torch.cat([un_pool, co_pool], dim=0)

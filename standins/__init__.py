@@ -5,4 +5,4 @@ path treats as injected components (reference elastic_diffusion.py:144-153) are 
 throughput runs.  The product (`elasticdiffusion-official_b200`) never imports this package.
 """
 from .models import *  # noqa: F401,F403
-from .models import StandInUNet, StubControlNet, StubTextEncoder, StubUNet, StubVAE, stub_text_embeds, timestep_embedding  # noqa: F401
+from .models import StandInControlNet, StandInUNet, StandInVAE, StubControlNet, StubTextEncoder, StubUNet, StubVAE, stub_text_embeds, timestep_embedding  # noqa: F401

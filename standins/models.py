@@ -320,6 +320,8 @@ class StandInUNet(nn.Module):
         else:
             self._build(preset, layers_per_block, head_dim, seed)
 
+    ENCODER_ONLY = False    # StandInControlNet: conv_in + down path + mid block only
+
     def _build(self, preset, layers_per_block, head_dim, seed):
         p = self.PRESETS[preset]
         widths, depths, ctx = p["widths"], p["depths"], p["ctx"]
@@ -351,6 +353,10 @@ class StandInUNet(nn.Module):
         self.mid1 = _ResBlock(c, c, temb)
         self.mid_attn = _Transformer2D(c, ctx, head_dim, p["mid_depth"])
         self.mid2 = _ResBlock(c, c, temb)
+        if self.ENCODER_ONLY:
+            self._build_control(chans, c, widths[0])
+            _seeded_(self, seed)
+            return
         self.up = nn.ModuleList()
         for i, (w, d) in reversed(list(enumerate(zip(widths, depths)))):
             for j in range(layers_per_block + 1):
@@ -364,7 +370,7 @@ class StandInUNet(nn.Module):
         self.conv_out = nn.Conv2d(c, 4, 3, padding=1)
         _seeded_(self, seed)
 
-    def forward(self, x, t, encoder_hidden_states=None, added_cond_kwargs=None, **kw):
+    def _embed(self, x, t, encoder_hidden_states, added_cond_kwargs):
         b = x.shape[0]
         t = torch.as_tensor(t, device=x.device).reshape(-1)
         if t.numel() == 1:
@@ -376,8 +382,10 @@ class StandInUNet(nn.Module):
             te = timestep_embedding(tid, self.add_time_dim).reshape(b, -1).to(dt)
             add = torch.cat([added_cond_kwargs["text_embeds"].to(dt), te], dim=-1)
             emb = emb + self.add_embedding.linear_2(F.silu(self.add_embedding.linear_1(add)))
-        ctx = encoder_hidden_states.to(dt)
-        h = self.conv_in(x.to(dt))
+        return emb, encoder_hidden_states.to(dt), dt
+
+    def _encode(self, h, emb, ctx):
+        """conv_in output -> (skip list, mid-block output)"""
         skips = [h]
         for mods in self.down:
             if mods[1] is None:
@@ -387,9 +395,124 @@ class StandInUNet(nn.Module):
                 h = h if isinstance(mods[1], nn.Identity) else mods[1](h, ctx)
             skips.append(h)
         h = self.mid2(self.mid_attn(self.mid1(h, emb), ctx), emb)
+        return skips, h
+
+    def forward(self, x, t, encoder_hidden_states=None, added_cond_kwargs=None, down_block_additional_residuals=None,
+                mid_block_additional_residual=None, **kw):
+        emb, ctx, dt = self._embed(x, t, encoder_hidden_states, added_cond_kwargs)
+        skips, h = self._encode(self.conv_in(x.to(dt)), emb, ctx)
+        # ControlNet residuals as diffusers' UNet2DConditionModel applies them (reference elastic_diffusion_w_controlnet.py
+        # :493-496 passes them through): one per skip connection + one for the mid block
+        if down_block_additional_residuals is not None:
+            skips = [s + r.to(s.dtype) for s, r in zip(skips, down_block_additional_residuals)]
+        if mid_block_additional_residual is not None:
+            h = h + mid_block_additional_residual.to(h.dtype)
         for res, attn, upc in self.up:
             h = res(torch.cat([h, skips.pop()], dim=1), emb)
             h = h if isinstance(attn, nn.Identity) else attn(h, ctx)
             if upc is not None:
                 h = upc(F.interpolate(h, scale_factor=2.0, mode="nearest"))
         return {"sample": self.conv_out(F.silu(self.norm_out(h)))}
+
+
+class StandInControlNet(StandInUNet):
+    """SD/SDXL-*shaped* random-weight ControlNet for throughput runs (cfg5): the UNet's encoder half (conv_in, down path,
+    mid block at the real widths / transformer depths) + the condition embedding (3 -> 16 -> 32 -> 96 -> 256 -> width0
+    3x3 convs, three of them stride 2: pixel resolution -> latent grid, like diffusers' ControlNetConditioningEmbedding)
+    + one 1x1 "zero conv" per skip connection and one for the mid block.  Call contract of the reference
+    (elastic_diffusion_w_controlnet.py:482-491): returns (down_block_res_samples, mid_block_res_sample)."""
+
+    ENCODER_ONLY = True
+
+    def _build_control(self, chans, c_mid, w0):
+        ce = [3, 16, 32, 96, 256]
+        self.cond_in = nn.Conv2d(3, 16, 3, padding=1)
+        self.cond_blocks = nn.ModuleList()
+        for a, b in zip(ce[1:-1], ce[2:]):
+            self.cond_blocks.append(nn.Conv2d(a, a, 3, padding=1))
+            self.cond_blocks.append(nn.Conv2d(a, b, 3, padding=1, stride=2))
+        self.cond_out = nn.Conv2d(256, w0, 3, padding=1)
+        self.zero_convs = nn.ModuleList([nn.Conv2d(c, c, 1) for c in chans])
+        self.mid_zero = nn.Conv2d(c_mid, c_mid, 1)
+
+    @property
+    def dtype(self):
+        return self.conv_in.weight.dtype
+
+    def forward(self, x, t, encoder_hidden_states=None, controlnet_cond=None, conditioning_scale=1.0, guess_mode=False,
+                return_dict=False, added_cond_kwargs=None):
+        emb, ctx, dt = self._embed(x, t, encoder_hidden_states, added_cond_kwargs)
+        c = F.silu(self.cond_in(controlnet_cond.to(dt)))
+        for blk in self.cond_blocks:
+            c = F.silu(blk(c))
+        skips, h = self._encode(self.conv_in(x.to(dt)) + self.cond_out(c), emb, ctx)
+        down = [z(s) * conditioning_scale for z, s in zip(self.zero_convs, skips)]
+        return down, self.mid_zero(h) * conditioning_scale
+
+
+# --------------------------------------------------------------------------------------------------------------
+# SD/SDXL-VAE-shaped decoder for decode-time measurements (tiled decode, cfg4) and the decode de-duplication study
+# --------------------------------------------------------------------------------------------------------------
+class _VaeRes(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.n1, self.c1 = nn.GroupNorm(32, cin), nn.Conv2d(cin, cout, 3, padding=1)
+        self.n2, self.c2 = nn.GroupNorm(32, cout), nn.Conv2d(cout, cout, 3, padding=1)
+        self.skip = nn.Conv2d(cin, cout, 1) if cin != cout else None
+
+    def forward(self, x):
+        h = self.c1(F.silu(self.n1(x)))
+        h = self.c2(F.silu(self.n2(h)))
+        return h + (x if self.skip is None else self.skip(x))
+
+
+class _VaeAttn(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.norm = nn.GroupNorm(32, c)
+        self.q, self.k, self.v, self.o = (nn.Linear(c, c) for _ in range(4))
+
+    def forward(self, x):
+        b, c, h, w = x.shape
+        y = self.norm(x).flatten(2).transpose(1, 2)
+        o = F.scaled_dot_product_attention(self.q(y)[:, None], self.k(y)[:, None], self.v(y)[:, None])[:, 0]
+        return x + self.o(o).transpose(1, 2).reshape(b, c, h, w)
+
+
+class StandInVAE(StubVAE):
+    """StubVAE whose `decode` is an SD/SDXL-VAE-*shaped* random-weight decoder: block_out_channels (128, 256, 512, 512),
+    3 ResNet layers per up block, single-head mid attention, GroupNorm(32) + SiLU, three nearest-2x upsamples (8x total) -
+    the public AutoencoderKL decoder topology.  `encode` stays the stub's (background strips only).  GroupNorm statistics
+    are per decoded tile, which is what makes tiled decoding differ from one whole-image decode."""
+
+    def __init__(self, widths=(128, 256, 512, 512), layers=3, seed=4321, scaling_factor=0.13025, force_upcast=True,
+                 device=None, dtype=None):
+        super().__init__(scaling_factor=scaling_factor, seed=seed, force_upcast=force_upcast)
+        self.config["block_out_channels"] = tuple(widths)
+        with torch.device(device or "cpu"):
+            c = widths[-1]
+            self.d_in = nn.Conv2d(4, c, 3, padding=1)
+            self.d_mid = nn.ModuleList([_VaeRes(c, c), _VaeAttn(c), _VaeRes(c, c)])
+            self.d_up = nn.ModuleList()
+            for i, w in enumerate(reversed(widths)):
+                blk = nn.ModuleList([_VaeRes(c if j == 0 else w, w) for j in range(layers)])
+                c = w
+                self.d_up.append(nn.ModuleList([blk, nn.Conv2d(w, w, 3, padding=1) if i < len(widths) - 1 else None]))
+            self.d_norm, self.d_out = nn.GroupNorm(32, c), nn.Conv2d(c, 3, 3, padding=1)
+        if device is not None:
+            self.to(device)
+        if dtype is not None:
+            self.to(dtype)
+        _seeded_(self, seed)
+
+    def decode(self, z, return_dict=True):
+        h = self.d_in(self.post_quant_conv(z))
+        for m in self.d_mid:
+            h = m(h)
+        for blk, up in self.d_up:
+            for r in blk:
+                h = r(h)
+            if up is not None:
+                h = up(F.interpolate(h, scale_factor=2.0, mode="nearest"))
+        out = self.d_out(F.silu(self.d_norm(h)))
+        return SimpleNamespace(sample=out) if return_dict else (out,)

@@ -244,3 +244,42 @@ def test_bench_algorithmic_byte_accounting_of_the_epilogue():
     # at most 4 owners per 2x2 cell (one per pixel), at least 1: between 2 and 8 elements per cell; ~7.2 for uniform picks
     assert 2 * cells < n <= 8 * cells and abs(n / cells - 7.2) < 0.2
     assert bench.needed_global_elements(geo, 8, idx, own, True) >= n
+
+
+# ---- all background strips precomputed before the loop in batched VAE encodes -------------------------
+@pytest.mark.parametrize("name", ["sd21_512x1024_T4_R4", "xl_768x2048_T2_R2_padded_views"])
+def test_strip_precompute_is_rng_neutral_and_batched(name):
+    """The precompute must (a) produce the strips the lazy per-miss path produces, (b) leave every generator exactly where
+    it found it, (c) need a handful of batched VAE encode calls instead of one per strip; the goldens (any mis-ordered
+    draw changes every later value) are reproduced with it switched on (test_wave_form_reproduces_goldens runs the
+    default = on) and off (here)."""
+    g = load_golden(name)
+    kw = oracle_kwargs(g["kwargs"])
+    outs, strips, calls = {}, {}, {}
+    for pre in (True, False):
+        ed = make_ed(g["sd_version"], g["view_batch_size"])
+        ed.precompute_strips = pre
+        ed.last_run = {}
+        ed.seed_everything(g["seed"])
+        outs[pre] = ws.denoise_wave_form(ed, **kw)
+        calls[pre] = ed.last_run.get("vae_encode_calls", 0)
+    assert (outs[True] - g["latent"]).abs().max().item() <= 2e-5 and (outs[False] - g["latent"]).abs().max().item() <= 2e-5
+    assert (outs[True] - outs[False]).abs().max().item() <= 2e-5
+    n_strips = {"sd21_512x1024_T4_R4": 2 * 4, "xl_768x2048_T2_R2_padded_views": (2 + 2) * 2}[name]
+    assert 1 <= calls[True] <= 2 and calls[False] == n_strips, calls
+    # generator state: a ledger's precompute between two draws does not change the second draw
+    ed = make_ed(g["sd_version"], g["view_batch_size"])
+    geo = geometry.build_geometry(1, 4, kw["height"] // 8, kw["width"] // 8, 128 if "XL" in g["sd_version"] else 64,
+                                  ed.get_downsample_size(kw["height"], kw["width"]), ed.view_config["window_size"],
+                                  ed.view_config["stride"], ed.view_config["context_size"])
+    ed.scheduler.set_timesteps(kw["num_inference_steps"])
+    torch.manual_seed(11)
+    np_state = __import__("numpy").random.get_state()[1].copy()
+    a0 = torch.rand(3)
+    want = torch.rand(3)
+    torch.manual_seed(11)
+    assert torch.equal(torch.rand(3), a0)
+    led = PKG.RngLedger(ed, geo)
+    assert led.precompute_strips(ed.scheduler.timesteps) >= 1 and len(led.strip_cache) == n_strips
+    assert torch.equal(torch.rand(3), want)
+    assert (__import__("numpy").random.get_state()[1] == np_state).all()
