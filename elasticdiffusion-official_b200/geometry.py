@@ -271,13 +271,20 @@ class TileGeometry:
     tables: dict
 
 
-def build_tiles(H, W, sample_size, scale, low_vram=False) -> TileGeometry:
+def build_tiles(H, W, sample_size, scale, low_vram=False, core=None, pad=None) -> TileGeometry:
     """Decode tiles of tiled_decode (ed:276-287): core = sample_size//4, stride = core, pad = sample_size//scale*3
-    (low_vram: stride = core//2, pad = core)."""
-    core = sample_size // 4
-    stride, pad = core, sample_size // scale * 3
-    if low_vram:
-        stride, pad = core // 2, core
+    (low_vram: stride = core//2, pad = core).  `core` / `pad` override the reference's sizes (stride = core): the opt-in
+    de-duplicated decode uses larger cores so that each pixel is decoded fewer times."""
+    if core is not None or pad is not None:
+        ref_core = sample_size // 4
+        core = int(core if core is not None else ref_core)
+        pad = int(pad if pad is not None else sample_size // scale * 3)
+        stride = core
+    else:
+        core = sample_size // 4
+        stride, pad = core, sample_size // scale * 3
+        if low_vram:
+            stride, pad = core // 2, core
     wins, ntr, ntc = sliding_windows(H, W, core, core, stride)
     flat = [v for w in wins for v in w]
     trf, trc = cover_ranges([wins[r * ntc][0] for r in range(ntr)], core, H)

@@ -134,6 +134,7 @@ class RngLedger:
         self.dev = owner.device
         self.rng_dev = owner.rng_device if owner.rng_device is not None else owner.device
         self.strip_cache = {}
+        self.host_ms = {"cells": 0.0, "drop": 0.0, "strips": 0.0, "undo": 0.0}   # host wall time per planner component
         self.n_cells = geo.lh * geo.lw
         self._rows = np.arange(self.n_cells)
         # device draws whose VALUES the host needs (drop masks, ed:541) run on a side stream so that reading them back
@@ -313,10 +314,11 @@ class RngLedger:
         final unconditional redraw); the bookkeeping runs in numpy, and once only cells with all four picks excluded
         remain invalid the remaining rounds are just their (parity-relevant) draws without index work."""
         n = self.n_cells
-        rows = self._rows
         idx = torch.randint(0, 4, (n,)).numpy()
-        bad = exclude[rows, idx]
-        m = int(bad.sum())
+        # only the still-invalid cells are re-examined each round (ascending cell order = the order the reference's
+        # boolean-mask assignment fills them in), so the work shrinks geometrically with the rounds
+        bad = np.flatnonzero(exclude[self._rows, idx])
+        m = bad.size
         rounds = 50
         hopeless = None
         while m > 0 and rounds > 0:
@@ -328,9 +330,10 @@ class RngLedger:
                 idx[bad] = last.numpy()
                 rounds = 0
                 break
-            idx[bad] = torch.randint(0, 4, (m,)).numpy()
-            bad = exclude[rows, idx]
-            m = int(bad.sum())
+            new = torch.randint(0, 4, (m,)).numpy()
+            idx[bad] = new
+            bad = bad[exclude[bad, new]]
+            m = bad.size
             rounds -= 1
         if m > 0:
             idx[bad] = torch.randint(0, 4, (m,)).numpy()
@@ -347,10 +350,15 @@ class RngLedger:
         prev = np.zeros(n, dtype=np.int64)                                         # k = 0: top-left pick (ed:536)
         strips = None
         thr = 100 * drop_p
+        tm, hm = time.perf_counter, self.host_ms
         for k in range(resampling_steps + 1):
             if k > 0:
+                t0 = tm()
                 idx = self._draw_cells(exclude)
+                t1 = tm()
                 drop = self._drop_draw()                                           # ed:541
+                hm["cells"] += 1e3 * (t1 - t0)
+                hm["drop"] += 1e3 * (tm() - t1)
                 # thresholds applied to the TORCH tensor like the reference: an int64 tensor against a Python float
                 # compares in float32, and 100 * drop_p is not always representable (0.8 -> 19.999999999999996)
                 drop[drop <= thr] = 0                                              # ed:542
@@ -359,7 +367,9 @@ class RngLedger:
                 prev = idx * drop + prev * (1 - drop)                              # ed:544
             exclude[rows, prev] = True                                             # ed:675
             out[k] = prev.astype(np.uint8)
+            t0 = tm()
             strips = self.pad_events(g.lh, g.lw, t)                                # unet_step of this iteration
+            hm["strips"] += 1e3 * (tm() - t0)
         return torch.from_numpy(out), strips
 
     def local_pass(self, t, view_batch_size):
@@ -373,8 +383,10 @@ class RngLedger:
 
     def undo_noise(self, n, shape, out):
         """The n = num_train/num_inference draws of undo_step (ed:695-701), in order."""
+        t0 = time.perf_counter()
         for k in range(n):
             out[k].copy_(torch.randn(shape, device=self.rng_dev, dtype=torch.float32), non_blocking=True)
+        self.host_ms["undo"] += 1e3 * (time.perf_counter() - t0)
         return out
 
 
@@ -442,6 +454,11 @@ class ElasticDiffusion(nn.Module):
         self._sym = None
         self._sym_decode = None
         self.unet_input_dtype = None  # dtype the gather kernels write the UNet batch in (None: fp32 like the reference)
+        # tiled decode: None = the reference's tiles (core = sample_size // 4, pad = 3 * sample_size // 8: every pixel is
+        # decoded 16x at SDXL); (core, pad) in latent units = opt-in de-duplicated decode with larger cores / smaller halos
+        # (row f1).  NOT result-preserving: GroupNorm statistics and the mid-block attention are per decoded tile
+        # (measured: profiles/r2_decode_dedup.json), so the default stays the reference geometry.
+        self.decode_tile_geometry = None
         self.precompute_strips = True  # background strips of all timesteps built before the loop in batched VAE encodes
         self.use_cuda_graphs = False  # capture each wave's UNet forward in a CUDA graph (static canvas / text buffers)
         self._graphs = {}
@@ -561,7 +578,8 @@ class ElasticDiffusion(nn.Module):
         L = native.lib()
         latents = latents.float().contiguous()
         B, C, H, W = latents.shape
-        tg = build_tiles(H, W, self.unet.config.sample_size, self.vae_scale_factor, self.low_vram)
+        dc, dp = self.decode_tile_geometry if self.decode_tile_geometry is not None else (None, None)
+        tg = build_tiles(H, W, self.unet.config.sample_size, self.vae_scale_factor, self.low_vram, core=dc, pad=dp)
         dev = latents.device
         tabs = {k: _i32(dev, v) for k, v in tg.tables.items()}
         T = tg.core + 2 * tg.pad
@@ -783,6 +801,8 @@ class ElasticDiffusion(nn.Module):
             self.vae.to(self.device)
         if needs_upcasting:
             self.upcast_vae()
+        if tiled_decoder == "dedup" and self.decode_tile_geometry is None:       # opt-in extension of the boolean flag
+            self.decode_tile_geometry = (self.unet.config.sample_size // 2, self.unet.config.sample_size // 4)
         decode_fn = self.tiled_decode if tiled_decoder else self.decode_latents
         if self.verbose and self._x0_log:
             x0s = torch.cat([decode_fn(z.to(self.device)) for z in self._x0_log]).clip(0, 1)
@@ -1023,6 +1043,7 @@ class ElasticDiffusion(nn.Module):
             if step_callback is not None:
                 step_callback(i, x)
         self.last_run["vae_encodes"] = len(ledger.strip_cache)
+        self.last_run["plan_host_ms_by_part"] = {k: round(v, 2) for k, v in ledger.host_ms.items()}
         return x, image_log
 
 

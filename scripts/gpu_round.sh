@@ -19,6 +19,12 @@ for s in $STAGES; do
            --roofline-cases "$CASES" > gpurun_out/ncu.log 2>&1; rc=$? ;;
     e2e) timeout 480 python -m pytest tests/test_gpu_e2e.py tests/test_gpu_zz_staged_in_pipeline.py -x -q > gpurun_out/t_e2e.log 2>&1; rc=$? ;;
     bench) timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench.err; rc=$? ;;
+    bench5) timeout 600 python bench.py --workload cfg5 --steps 5 --warmup 3 --no-extras > gpurun_out/bench_cfg5_n1.json 2> gpurun_out/bench_cfg5.err; rc=$? ;;
+    bench4) timeout 900 python bench.py --workload cfg4 --steps 5 --warmup 3 --no-extras > gpurun_out/bench_cfg4_n1.json 2> gpurun_out/bench_cfg4.err; rc=$? ;;
+    bench2) timeout 600 python bench.py --workload cfg2 --steps 5 --warmup 3 --no-extras > gpurun_out/bench_cfg2_n1.json 2> gpurun_out/bench_cfg2.err; rc=$? ;;
+    minb8) ED_NVCC_FLAGS="-DED_HALF_MINB=8" python -c "import importlib; importlib.import_module('elasticdiffusion-official_b200').native.build(force=True)" && \
+           timeout 240 python bench.py --roofline-only --roofline-cases 'ed_wave_epilogue+rrg(wave2:R1=1),ed_wave_epilogue(wave2:R1=1)' > gpurun_out/roofline_minb8.json 2> gpurun_out/roofline_minb8.err; rc=$?; \
+           python -c "import importlib; importlib.import_module('elasticdiffusion-official_b200').native.build(force=True)" ;;
     benchref) timeout 900 python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; rc=$? ;;
     probe) timeout 600 python scripts/probe_unet.py gpurun_out/probe_unet.json > gpurun_out/probe_unet.log 2>&1; rc=$? ;;
     launches) BENCH_GRAPHS=0 BENCH_CUPROF=1 timeout 420 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 5000 --csv \
@@ -37,4 +43,6 @@ for f in t_gpu t_kernels t_peer t_e2e; do [ -f gpurun_out/$f.log ] && tail -4 gp
 [ -f gpurun_out/bench_n1.json ] && head -c 1500 gpurun_out/bench_n1.json
 [ -f gpurun_out/bench.err ] && tail -5 gpurun_out/bench.err
 [ -f gpurun_out/bench_ref.json ] && head -c 600 gpurun_out/bench_ref.json
+for f in bench_cfg5 bench_cfg4 bench_cfg2; do [ -f gpurun_out/$f.err ] && tail -3 gpurun_out/$f.err; done
+[ -f gpurun_out/roofline_minb8.json ] && cat gpurun_out/roofline_minb8.json
 true

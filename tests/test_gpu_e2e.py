@@ -142,6 +142,31 @@ def test_product_tiled_decode_matches_oracle(low_vram):
     assert (img - want).abs().max().item() < 1e-5
 
 
+def test_dedup_decode_geometry_is_the_same_algorithm_with_larger_cores():
+    """SURVEY 8 row f1 (opt-in, default off): `decode_tile_geometry = (core, pad)` runs the reference's blend algorithm
+    (ed:287-308) on a different tile grid through the same kernels; checked against the torch restatement of that tiling.
+    With the stub VAE (no normalisation layers) and a halo covering its receptive field the image equals the reference
+    tiling's; with a GroupNorm decoder it does not (scripts/decode_dedup_study.py, profiles/r2_decode_dedup.json)."""
+    import torch.nn.functional as F
+    ed = make_ed("XL1.0", 4, "cuda")
+    z = torch.randn(1, 4, 256, 256, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    ref_img = ed.tiled_decode(z)                                   # reference tiles: core 32, pad 48 -> 64 tiles
+    n_ref = ed.last_run["decode_tiles"]
+    ed.decode_tile_geometry = (64, 16)                              # 16 tiles of 96^2 latent: 2.25x instead of 16x decoded
+    ed.last_run = {}
+    img = ed.tiled_decode(z)
+    assert (n_ref, ed.last_run["decode_tiles"]) == (64, 16)
+    core, pad, s = 64, 16, 8
+    zp = F.pad(z, (pad, pad, pad, pad))
+    want = torch.zeros_like(img)
+    for h0 in range(0, 256, core):
+        for w0 in range(0, 256, core):
+            dec = ed.decode_latents(zp[:, :, h0:h0 + core + 2 * pad, w0:w0 + core + 2 * pad])
+            want[:, :, h0 * s:(h0 + core) * s, w0 * s:(w0 + core) * s] = dec[:, :, pad * s:(pad + core) * s, pad * s:(pad + core) * s]
+    assert (img - want).abs().max().item() < 1e-5
+    assert (img - ref_img).abs().max().item() < 1e-5               # stub VAE: receptive field << halo, no GroupNorm
+
+
 def test_verbose_mode_logs_intermediate_x0_grid():
     ed = make_ed("2.1", 4, "cuda")
     ed.verbose, ed.log_freq, ed.autocast = True, 1, False
