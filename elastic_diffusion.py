@@ -17,3 +17,6 @@ ConstScheduler = _pkg.ConstScheduler
 TimeIt = _pkg.TimeIt
 timelog = _pkg.timelog
 package = _pkg
+
+if __name__ == '__main__':   # same flags / outputs as the reference's command line (elastic_diffusion.py:1134-1210)
+    _il.import_module("elasticdiffusion-official_b200.cli").main(ElasticDiffusion, timelog)

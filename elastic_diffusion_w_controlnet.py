@@ -12,3 +12,6 @@ _cn = _il.import_module("elasticdiffusion-official_b200.controlnet")
 ElasticDiffusion = _cn.ElasticDiffusion
 CosineScheduler, LinearScheduler, ConstScheduler = _cn.CosineScheduler, _cn.LinearScheduler, _cn.ConstScheduler
 TimeIt, timelog = _cn.TimeIt, _cn.timelog
+
+if __name__ == '__main__':   # same flags / outputs as the twin's command line (elastic_diffusion_w_controlnet.py:1342-1436)
+    _il.import_module("elasticdiffusion-official_b200.cli").main(ElasticDiffusion, timelog, twin=True)

@@ -453,6 +453,7 @@ class ElasticDiffusion(nn.Module):
                                       # epilogue over NVLink (no collective), "nccl" = all_gather_into_tensor per wave
         self._sym = None
         self._sym_decode = None
+        self._low_vram_limit = None
         self.unet_input_dtype = None  # dtype the gather kernels write the UNet batch in (None: fp32 like the reference)
         # tiled decode: None = the reference's tiles (core = sample_size // 4, pad = 3 * sample_size // 8: every pixel is
         # decoded 16x at SDXL); (core, pad) in latent units = opt-in de-duplicated decode with larger cores / smaller halos
@@ -705,7 +706,10 @@ class ElasticDiffusion(nn.Module):
         n = canvas.shape[0]
         per, lo, hi = shard_range(n, ws, rank)
         outs = []
-        limit = self.unet_batch_limit or max(hi - lo, 1)
+        # samples per UNet call: the whole (rank-local part of the) wave by default.  `view_batch_size` is the reference's
+        # memory knob for the view passes (ed:830-850, its global passes are always batch 2B): it is honoured as the
+        # batch bound when the caller asked for the memory-saving mode (low_vram) or set `unet_batch_limit` explicitly.
+        limit = self.unet_batch_limit or (self._low_vram_limit if self.low_vram else None) or max(hi - lo, 1)
         for s in range(lo, hi, limit):
             e = min(s + limit, hi)
             kw = {}
@@ -777,6 +781,77 @@ class ElasticDiffusion(nn.Module):
             self.exchange = "nccl"
             return {}
 
+    # -- verbose-mode diagnostics (ed:759-796, 1093-1118): plain torch, outside the hot path -----------------------------------
+    @torch.no_grad()
+    def generate(self, latent, text_embeds, add_text_embeds, guidance_scale=7.5):
+        """ed:759-796: a plain CFG + DDIM run on the (low-resolution) latent, logged as `global_img` in verbose mode.
+        Every UNet call pads the latent to the native size with the background strips of the timestep (ed:405-408)."""
+        vb = getattr(self, "_verbose", None)
+        if vb is None or vb.get("ledger") is None:
+            raise RuntimeError("generate() replays the run's background strips: call it after generate_image(verbose=True)")
+        ledger, inter = vb["ledger"], []
+        B = latent.shape[0]
+        nat = ledger.geo.native
+        xl = self.sd_version.startswith('XL')
+        if self.low_vram:
+            self.vae.cpu()
+            self.unet.to(self.device)
+        for i, t in enumerate(tqdm(self.scheduler.timesteps)):
+            x2 = torch.cat([latent] * 2)
+            left, right, top, bottom = ledger.pad_events(latent.shape[-2], latent.shape[-1], t)     # ed:405-408, 366-391
+            lp, _ = pad_split(nat, latent.shape[-1])
+            tp, _ = pad_split(nat, latent.shape[-2])
+            ex = lambda s: s.to(x2.dtype).expand(x2.shape[0], -1, -1, -1)
+            if left is not None or right is not None:
+                x2 = torch.cat(([ex(left)] if left is not None else []) + [x2] + ([ex(right)] if right is not None else []), dim=3)
+            if top is not None or bottom is not None:
+                x2 = torch.cat(([ex(top)] if top is not None else []) + [x2] + ([ex(bottom)] if bottom is not None else []), dim=2)
+            kw = {}
+            if xl:
+                ids = self._get_add_time_ids(self.default_size, (0, 0), self.default_size, dtype=text_embeds.dtype)
+                kw["added_cond_kwargs"] = {"text_embeds": add_text_embeds, "time_ids": ids.to(self.device).repeat(2 * B, 1)}
+            with torch.autocast("cuda", enabled=self.autocast):
+                eps = self.unet(x2, t, encoder_hidden_states=text_embeds, **kw)["sample"]
+            eps = eps[:, :, tp:tp + latent.shape[-2], lp:lp + latent.shape[-1]]
+            un, co = eps.chunk(2)
+            eps = un + guidance_scale * (co - un)
+            sc = {k: torch.tensor(v, dtype=torch.float32, device=latent.device) for k, v in step_scalars(self.scheduler, t).items()}
+            x0 = (latent - sc["sqrt_beta_t"] * eps) / sc["sqrt_alpha_t"]
+            latent = sc["sqrt_alpha_prev"] * x0 + sc["sqrt_dir"] * eps
+            if i % self.log_freq == 0:
+                inter.append(x0.float().cpu())
+        needs_upcasting = self.vae.dtype == torch.float16 and self.vae.config.force_upcast
+        if self.low_vram:
+            self.unet.cpu()
+            self.vae.to(self.device)
+        if needs_upcasting:
+            self.upcast_vae()
+        img = _to_pil(self.decode_latents(latent.float())[0])
+        if needs_upcasting:
+            self.vae.to(dtype=torch.float16)
+        return img, {"inter_x0": inter}
+
+    def _rrg_reference_x0(self, geo, x_in, out, idx_dev, owner, R1, B, g, sc, fp16sem):
+        """cascade_info['x0'] of reduced_resolution_guidance (ed:909-921) for the verbose log: the low-res DDIM x0 the fused
+        epilogue evaluates per cell, restated with torch ops from the same inputs."""
+        dev = x_in.device
+        T_ = lambda k: torch.tensor(geo.tables[k], dtype=torch.long, device=dev)
+        lp, rp, tp, bp = geo.g_pad
+        lh, lw, C = geo.lh, geo.lw, geo.C
+        f32 = lambda v: torch.tensor(v, dtype=torch.float32, device=dev)
+        kl = R1 - 1
+        pick = idx_dev[kl].long().view(lh, lw)
+        r, c = torch.arange(lh, device=dev)[:, None], torch.arange(lw, device=dev)[None, :]
+        xl = x_in[:, :, T_("row_src")[2 * r + pick // 2], T_("col_src")[2 * c + pick % 2]]
+        glob = out[:2 * B * R1].reshape(R1, 2, B, C, geo.native, geo.native)[..., tp:tp + lh, lp:lp + lw].float()
+        ksel = owner.view(geo.H, geo.W).long()[T_("down_row")][:, T_("down_col")]                    # (lh, lw)
+        pickk = lambda s: torch.gather(glob[:, s], 0, ksel[None, None, None].expand(1, B, C, lh, lw))[0]
+        d = pickk(1) - pickk(0)
+        rnd = (lambda v: v.half().float()) if fp16sem else (lambda v: v)
+        gl = rnd(f32(g) * rnd(d))
+        el = rnd(glob[kl, 0] + gl)
+        return (xl - rnd(f32(sc["sqrt_beta_t"]) * el)) / f32(sc["sqrt_alpha_t"])
+
     @torch.no_grad()
     def generate_image(self, prompts, negative_prompts='',
                        height=768, width=768,
@@ -804,9 +879,21 @@ class ElasticDiffusion(nn.Module):
         if tiled_decoder == "dedup" and self.decode_tile_geometry is None:       # opt-in extension of the boolean flag
             self.decode_tile_geometry = (self.unet.config.sample_size // 2, self.unet.config.sample_size // 4)
         decode_fn = self.tiled_decode if tiled_decoder else self.decode_latents
-        if self.verbose and self._x0_log:
-            x0s = torch.cat([decode_fn(z.to(self.device)) for z in self._x0_log]).clip(0, 1)
-            image_log['intermediate_x0_imgs'] = _to_pil(_grid(x0s))
+        if self.verbose:                                                                       # ed:1093-1118
+            vb = self._verbose
+            if vb.get("init_low") is not None:
+                image_log['global_img'], info = self.generate(vb["init_low"], vb["text"], vb["pooled"],
+                                                              guidance_scale=guidance_scale)
+                if info.get('inter_x0'):
+                    x0s = torch.cat([decode_fn(z.to(self.device)) for z in info['inter_x0']])
+                    image_log['global_img_inter_x0_imgs'] = _to_pil(_grid(x0s))
+            if self._x0_log:
+                x0s = torch.cat([decode_fn(z.to(self.device)) for z in self._x0_log]).clip(0, 1)
+                image_log['intermediate_x0_imgs'] = _to_pil(_grid(x0s))
+            image_log['intermediate_cascade_x0_imgs'] = {}
+            if vb.get("cascade"):
+                x0s = torch.cat([decode_fn(z.to(self.device)) for z in vb["cascade"]])
+                image_log['intermediate_cascade_x0_imgs']['rrg'] = _to_pil(_grid(x0s))
         imgs = torch.cat([decode_fn(latent[i:i + 1]) for i in range(len(latent))])   # ed:1121 (one sample at a time)
         if grid:
             imgs = [_grid(imgs)]
@@ -832,6 +919,8 @@ class ElasticDiffusion(nn.Module):
         self._shard_dtype = None
         self._sym = None
         self._x0_log = []
+        self._verbose = {}
+        self._low_vram_limit = max(2, int(self.view_batch_size)) * (1 if isinstance(prompts, str) else len(prompts))
         ds = self.get_downsample_size(height, width)                                           # ed:968
         self.default_size = (4 * height, 4 * width)                                            # ed:969
         T = num_inference_steps
@@ -1017,6 +1106,11 @@ class ElasticDiffusion(nn.Module):
             idx_ev[p["slot"]].record()
             t_dev.fill_(int(t))
 
+            if self.verbose and i == 0:                # init_downsampled_latent (ed:677-678): the k = 0 (top-left) picks
+                rs = torch.tensor(geo.tables["row_src"][0::2], device=dev)
+                cs = torch.tensor(geo.tables["col_src"][0::2], device=dev)
+                self._verbose = dict(init_low=x[:, :, rs][:, :, :, cs].clone(), text=text_pair, pooled=pool_pair, ledger=ledger,
+                                     cascade=[])
             # ---- wave 1 ----------------------------------------------------------------------------------------------------
             prm = native.StepParams(guidance=guidance_scale, rrg_weight=float(w), rrg_norm=rrg_norm, R1=R + 1, **sc)
             if repaint:
@@ -1030,10 +1124,16 @@ class ElasticDiffusion(nn.Module):
                 # ---- wave 2 (repaint: one more estimate at the re-noised latent, guidance / 3; ed:1041-1056) --------
                 prm2 = native.StepParams(guidance=guidance_scale / 3, rrg_weight=float(w), rrg_norm=rrg_norm, R1=1, **sc)
                 prm2.flags = native.FLAG_RRG if rrg_on else 0
-                run_wave(x_mid, t, idx2, 1, strips_g2, strips_v2, prm2, 1, None, x_next, x0_buf, text2, pool2)
+                out_w = run_wave(x_mid, t, idx2, 1, strips_g2, strips_v2, prm2, 1, None, x_next, x0_buf, text2, pool2)
+                rrg_in = (x_mid, idx2, owner2, 1, prm2)
             else:
                 prm.flags = native.FLAG_RRG if rrg_on else 0
-                run_wave(x, t, idx1, R + 1, strips_g, strips_v, prm, 0, None, x_next, x0_buf, text1, pool1)
+                out_w = run_wave(x, t, idx1, R + 1, strips_g, strips_v, prm, 0, None, x_next, x0_buf, text1, pool1)
+                rrg_in = (x, idx1, owner1 if R > 0 else owner2, R + 1, prm)
+            if self.verbose and rrg_on and i % self.log_freq == 0 and torch.is_tensor(out_w):   # ed:1074-1077 (not when sharded)
+                xi, ix, ow, r1, pr = rrg_in
+                self._verbose["cascade"].append(self._rrg_reference_x0(
+                    geo, xi, out_w, ix, ow, r1, B, pr.guidance, sc, bool(pr.flags & native.FLAG_FP16_SEM)).cpu())
             if i + 1 < n_steps:
                 nxt = plan_step(i + 1)          # look-ahead: host RNG chain of the next step runs under this step's GPU work
             x, x_next = x_next, x                                                              # ed:1078

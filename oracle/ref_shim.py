@@ -72,6 +72,11 @@ def load_reference_module(name="elastic_diffusion"):
     spec = importlib.util.spec_from_file_location("_ref_" + name, path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
+    # the reference calls torchvision's make_grid(..., nrows=...) (ed:1099-1124): with its pinned torchvision 0.12 the unknown
+    # keyword falls into **kwargs and is ignored (nrow stays 8); the installed torchvision rejects it.  Same behaviour here:
+    if hasattr(mod, "make_grid"):
+        tv_make_grid = mod.make_grid
+        mod.make_grid = lambda tensor, *a, nrows=None, **k: tv_make_grid(tensor, *a, **k)
     _cached[name] = mod
     return mod
 
@@ -125,4 +130,7 @@ def run_reference(o, **gen_kwargs):
         imgs, log = o.generate_image(**gen_kwargs)
     finally:
         o.decode_latents, o.tiled_decode = dec, tdec
-    return imgs, log, (torch.cat(chunks) if chunks else None)
+    # the final latents are decoded last, one prompt at a time (ed:1121); verbose mode decodes its logging latents before
+    prompts = gen_kwargs.get("prompts", "")
+    n = 1 if isinstance(prompts, str) else len(prompts)
+    return imgs, log, (torch.cat(chunks[-n:]) if chunks else None)

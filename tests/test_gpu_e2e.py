@@ -173,6 +173,40 @@ def test_verbose_mode_logs_intermediate_x0_grid():
     ed.seed_everything(0)
     imgs, log = ed.generate_image("a", "b", height=512, width=768, num_inference_steps=2, resampling_steps=1, **NOBAR)
     assert "intermediate_x0_imgs" in log and imgs[0].size == (768, 512)
+    assert {"global_img", "global_img_inter_x0_imgs", "intermediate_cascade_x0_imgs"} <= set(log)
+
+
+def test_verbose_image_log_matches_the_reference():
+    """ed:1093-1118: global_img (a plain run on the first low-res latent, ed:759-796), its intermediate x0 grid, the
+    per-step x0 grid and the RRG reference x0 grid - same keys, same image sizes, same pixels (up to the 8-bit rounding of
+    values that differ in the last float bits) as the unmodified reference run on CPU with the same seeds."""
+    import numpy as np
+    from oracle.ddim_restated import DDIMRestated
+    from oracle.ref_shim import build_reference, reference_available, run_reference
+    if not reference_available():
+        pytest.skip("unmodified reference not installed (baseline/_ref)")
+    from conftest import components
+    kw = dict(prompts="a cat", negative_prompts="blurry", height=512, width=1024, num_inference_steps=3, resampling_steps=2,
+              guidance_scale=10.0, new_p=0.3, rrg_stop_t=0.2, rrg_init_weight=1000, cosine_scale=10.0, repaint_sampling=True)
+    unet, vae, txt, proj = components("2.1")
+    o = build_reference(unet, vae, DDIMRestated(), txt, sd_version="2.1", view_batch_size=4, verbose=True)
+    o.log_freq = 1
+    o.seed_everything(0)
+    ref_imgs, ref_log, _ = run_reference(o, progress=lambda it: it, **kw)
+    ed = make_ed("2.1", 4, "cuda")
+    ed.verbose, ed.log_freq, ed.autocast, ed.rng_device = True, 1, False, torch.device("cpu")
+    ed.seed_everything(0)
+    imgs, log = ed.generate_image(**kw, **NOBAR)
+    assert set(log) == set(ref_log) and set(log["intermediate_cascade_x0_imgs"]) == set(ref_log["intermediate_cascade_x0_imgs"])
+
+    def close(a, b, what):
+        assert a.size == b.size, (what, a.size, b.size)
+        d = np.abs(np.asarray(a).astype(np.int32) - np.asarray(b).astype(np.int32))
+        assert d.max() <= 1 and (d > 0).mean() < 0.01, (what, d.max(), (d > 0).mean())
+    close(imgs[0], ref_imgs[0], "image")
+    for k in ("global_img", "global_img_inter_x0_imgs", "intermediate_x0_imgs"):
+        close(log[k], ref_log[k], k)
+    close(log["intermediate_cascade_x0_imgs"]["rrg"], ref_log["intermediate_cascade_x0_imgs"]["rrg"], "cascade")
 
 
 @pytest.mark.parametrize("name", cn_golden_names())

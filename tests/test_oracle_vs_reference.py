@@ -1,5 +1,7 @@
 """CPU, build container only: the oracle against the LIVE unmodified reference (skipped where /root/reference is
 absent, e.g. on the GPU box - there the committed goldens stand in)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -150,3 +152,60 @@ def test_sizes_not_divisible_by_8_are_floored():
     ed.seed_everything(0)
     got = ws.denoise_wave_form(ed, height=516, width=1028, **kw)
     assert (got - want).abs().max().item() <= 2e-5
+
+
+@pytest.mark.parametrize("fname,twin", [("elastic_diffusion.py", False), ("elastic_diffusion_w_controlnet.py", True)])
+def test_cli_flags_and_defaults_match_the_reference_command_line(fname, twin):
+    """ed:1134-1161 / cn:1342-1372: every `--flag` of the reference's __main__ parser exists in the drop-in module's parser
+    with the same type and default (the reference's parser lives under `if __name__ == '__main__'`, so its source text is
+    read, not imported)."""
+    import ast
+    import importlib
+    from oracle.ref_shim import reference_dir
+    tree = ast.parse(open(os.path.join(reference_dir(), fname)).read())
+    cli = importlib.import_module("elasticdiffusion-official_b200.cli")
+    mine = {a.dest: a for a in cli.build_parser(twin)._actions if a.option_strings and a.dest != "help"}
+    seen = 0
+    for node in ast.walk(tree):
+        if not (isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr == "add_argument"):
+            continue
+        flag = node.args[0].value.lstrip("-")
+        kws = {k.arg: k.value for k in node.keywords}
+        assert flag in mine, flag
+        assert mine[flag].type.__name__ == kws["type"].id, (flag, kws["type"].id, mine[flag].type)
+        assert mine[flag].default == ast.literal_eval(kws["default"]), (flag, mine[flag].default)
+        if "choices" in kws and flag == "sd_version":
+            assert list(mine[flag].choices) == ast.literal_eval(kws["choices"])
+        seen += 1
+    assert seen == len(mine) == (27 if twin else 24), (seen, len(mine))
+
+
+def test_process_condition_image_matches_the_twin():
+    """cn:1102-1117 (canny / depth pre-processing, outside the hot path) with stand-ins for cv2.Canny and the depth
+    estimator: same PIL image out of the drop-in class and the unmodified twin."""
+    import sys
+    import types
+    from PIL import Image
+    from conftest import PKG
+    import standins
+    fake_cv2 = sys.modules.get("cv2") or types.ModuleType("cv2")
+    had = hasattr(fake_cv2, "Canny")
+    if not had:
+        fake_cv2.Canny = lambda img, lo, hi: (np.asarray(img)[:, :, 0] > (lo + hi) // 2).astype(np.uint8) * 255
+        sys.modules["cv2"] = fake_cv2
+    try:
+        unet, vae, txt, proj = components("2.1")
+        o = build_reference(unet, vae, DDIMRestated(), txt, sd_version="2.1", controlnet=standins.StubControlNet())
+        ed = PKG.controlnet.ElasticDiffusion.from_components("cpu", unet, vae, None, txt, sd_version="2.1",
+                                                             controlnet=standins.StubControlNet())
+        depth = lambda im: {"depth": Image.fromarray((np.asarray(im)[:, :, 1] // 2).astype(np.uint8))}
+        o.depth_estimator = ed.depth_estimator = depth
+        img = Image.fromarray(np.random.RandomState(0).randint(0, 255, (64, 96, 3), dtype=np.uint8))
+        for model in ("canny", "depth"):
+            a, b = o.process_condition_image(img, model), ed.process_condition_image(img, model)
+            assert a.size == b.size and a.mode == b.mode and np.array_equal(np.asarray(a), np.asarray(b)), model
+        with pytest.raises(AssertionError):
+            ed.process_condition_image(img, "pose")
+    finally:
+        if not had:
+            del fake_cv2.Canny
