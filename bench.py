@@ -732,6 +732,7 @@ def main():
                      "exchange": ed.exchange, "exchange_fallback": ed.last_run.get("exchange_fallback")},
             # host side: the look-ahead RNG planner (runs under the previous step's GPU work) and the background strips
             "host": {"plan_ms_per_step": round(ed.last_run.get("plan_host_ms", 0.0) / max(ed.last_run["steps"], 1), 3),
+                     "throttle_wait_ms_per_step": round(ed.last_run.get("throttle_wait_ms", 0.0) / max(ed.last_run["steps"], 1), 3),
                      "plan_ms_by_part_total": ed.last_run.get("plan_host_ms_by_part"),
                      "strips": ed.last_run.get("vae_encodes", 0), "vae_encode_calls": ed.last_run.get("vae_encode_calls", 0)},
             "kernels_in_step": {k: {"launches": n, "avg_us": round(1e3 * ms / max(n, 1), 2)} for k, (n, ms) in ktimes.items()},

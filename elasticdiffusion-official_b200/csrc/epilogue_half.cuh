@@ -22,6 +22,7 @@
 #pragma once
 #include "epilogue_staged.cuh"
 
+#define HALF_THREADS 128   // threads per CTA of the half kernels (the per-thread slot stride of the R1 > 1 kernel depends on it)
 #ifndef ED_HALF_MINB
 #define ED_HALF_MINB 6   // resident 128-thread CTAs per SM the R1 == 1 kernel is compiled for (register cap 65536 / (128 * MINB))
 #endif
@@ -170,7 +171,7 @@ ED_DEVICE void half_body(const EpiArgs& A, int xg, int yr, uint8_t* smem_slots) 
   // nearest-DOWNsampling reads for the cell (ed:688)
   unsigned picks = 0;
   if constexpr (RRG) picks = __ldg(reinterpret_cast<const unsigned*>(A.idx + (long long)(R1 - 1) * P.lh * P.lw + cell0));
-  OT* slots = reinterpret_cast<OT*>(smem_slots);   // [2*R1][threads][4] : slot (ks) of this thread at (ks * threads + tid) * 4
+  OT* slots = reinterpret_cast<OT*>(smem_slots);   // [2*R1][HALF_THREADS][4]
 
   // one (b, c) plane of the thread's tile; returns true when a quotient left the fast division's range
   auto plane_tile = [&](int z, auto exact_tag) -> bool {
@@ -202,32 +203,44 @@ ED_DEVICE void half_body(const EpiArgs& A, int xg, int yr, uint8_t* smem_slots) 
         }
       }
     } else {
-      // all 2*R1 (iteration, uncond/cond) score vectors of the 4 cells: independent 8-byte loads -> private smem slots
-      const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+      // all 2*R1 (iteration, uncond/cond) score vectors of the 4 cells: independent 8-byte (fp32: 16-byte) loads -> this
+      // thread's private shared-memory slots (no barrier).  Slot stride between consecutive (iteration, s) vectors is the
+      // compile-time constant HALF_THREADS * 4 elements, so once a pixel's owner is folded into its base pointer the
+      // (uncond, cond) picks are two loads at immediate offsets.  Within a warp the slots are interleaved (lane l ->
+      // slot 2 (l % 16) + l / 16) so that the 16-bit picks of the 32 lanes fall into 32 different banks.
+      constexpr int KS = HALF_THREADS * 4;                       // elements between the vectors of ks and ks + 1
+      const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+      const int slot = (tid & ~31) | ((tid & 15) << 1) | ((tid >> 4) & 1);
+      OT* mine = slots + slot * 4;
       for (int ks = 0; ks < 2 * R1; ++ks) {
         const OT* src = sample(ks * P.B + b) + c * plane + doff;
         if constexpr (sizeof(OT) == 4)
-          *reinterpret_cast<float4*>(slots + ((size_t)ks * nthr + tid) * 4) = __ldg(reinterpret_cast<const float4*>(src));
+          *reinterpret_cast<float4*>(mine + ks * KS) = __ldg(reinterpret_cast<const float4*>(src));
         else
-          *reinterpret_cast<uint2*>(slots + ((size_t)ks * nthr + tid) * 4) = __ldg(reinterpret_cast<const uint2*>(src));
+          *reinterpret_cast<uint2*>(mine + ks * KS) = __ldg(reinterpret_cast<const uint2*>(src));
       }
-      auto score = [&](int k, int s, int q) -> float { return to_f32<OT>(slots[((size_t)(2 * k + s) * nthr + tid) * 4 + q]); };
+      float lun[4], lco[4];                                      // scores of the owner at pixel (2r, 2c) = row 0, even column
 #pragma unroll
       for (int r = 0; r < 2; ++r)
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const float d = round_f16<F16>(__fsub_rn(score(own[r][e], 1, e >> 1), score(own[r][e], 0, e >> 1)));
+          const OT* pk = mine + own[r][e] * (2 * KS) + (e >> 1);  // (owner, uncond) of this pixel's cell; cond is KS further
+          const float un = to_f32<OT>(pk[0]), co = to_f32<OT>(pk[KS]);
+          if (r == 0 && (e & 1) == 0) {
+            lun[e >> 1] = un;
+            lco[e >> 1] = co;
+          }
+          const float d = round_f16<F16>(__fsub_rn(co, un));
           gd[r][e] = round_f16<F16>(__fmul_rn(K.g, d));
         }
       if constexpr (RRG) {
+        const OT* last = mine + (R1 - 1) * (2 * KS);             // uncond scores of the last iteration (ed:910-918)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const unsigned p = (picks >> (8 * q)) & 3u;
           const float top = (p & 1u) ? xin[0][2 * q + 1] : xin[0][2 * q];
           const float bot = (p & 1u) ? xin[1][2 * q + 1] : xin[1][2 * q];
-          const int kd = own[0][2 * q];                                                   // owner at pixel (2r, 2c)
-          rx0[q] = half_low_res_x0<F16, EXACT>((p & 2u) ? bot : top, score(R1 - 1, 0, q), score(kd, 0, q), score(kd, 1, q),
-                                               K.g, K.sb, K.div_sa, bad);
+          rx0[q] = half_low_res_x0<F16, EXACT>((p & 2u) ? bot : top, to_f32<OT>(last[q]), lun[q], lco[q], K.g, K.sb, K.div_sa, bad);
         }
       }
     }
@@ -243,7 +256,7 @@ ED_DEVICE void half_body(const EpiArgs& A, int xg, int yr, uint8_t* smem_slots) 
 // The step's flags live in DEVICE memory (a captured launch is replayed with new parameters), so RRG / fp16 semantics are
 // CTA-uniform run-time branches into four specialised bodies rather than launch-time template arguments.
 template <typename OT, bool MULTI, bool PEER>
-__global__ void __launch_bounds__(128, MULTI ? 4 : ED_HALF_MINB) wave_epilogue_half_kernel(const EpiArgs A) {
+__global__ void __launch_bounds__(HALF_THREADS, MULTI ? 4 : ED_HALF_MINB) wave_epilogue_half_kernel(const EpiArgs A) {
   ED_DYN_SMEM(smem_raw);
   const int xg = blockIdx.x * blockDim.x + threadIdx.x;   // group of 8 columns
   const int yr = blockIdx.y * blockDim.y + threadIdx.y;   // row pair = low-res row
@@ -273,12 +286,12 @@ static inline HalfCfg half_config(const ed_plan_t& P, int R1, int so) {
   int bx = 32;
   while (bx > 1 && bx / 2 >= wg) bx /= 2;
   c.bx = bx;
-  c.by = 128 / bx;
+  c.by = HALF_THREADS / bx;
   c.grid_x = (wg + bx - 1) / bx;
   c.grid_y = (hr + c.by - 1) / c.by;
   const long long nz = (long long)P.B * P.C;
   c.grid_z = nz > 65535 ? 65535 : (int)nz;
-  c.smem = R1 > 1 ? (size_t)128 * 2 * R1 * 4 * so : 0;
+  c.smem = R1 > 1 ? (size_t)HALF_THREADS * 2 * R1 * 4 * so : 0;
   c.ok = c.smem <= 200 * 1024;
   return c;
 }

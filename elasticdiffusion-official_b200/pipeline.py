@@ -1079,7 +1079,13 @@ class ElasticDiffusion(nn.Module):
             p["strips_v"] = ledger.local_pass(t, self.view_batch_size)                          # ed:1027
             slot = i % 3
             if idx_ev[slot] is not None:
-                idx_ev[slot].synchronize()             # the H2D copy that last used this pinned buffer has run
+                # the H2D copy that last used this pinned buffer has run.  This is also what keeps the host at most ~3 steps
+                # ahead of the GPU: the wait is throttling, not planner work, and is accounted separately
+                t_w = time.perf_counter()
+                idx_ev[slot].synchronize()
+                t_w = time.perf_counter() - t_w
+                t_host += t_w
+                self.last_run["throttle_wait_ms"] = self.last_run.get("throttle_wait_ms", 0.0) + 1e3 * t_w
             idx_pin[slot].copy_(idx_host)
             p["slot"] = slot
             if repaint:
