@@ -121,6 +121,14 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t phase)
   }
   asm volatile("trap;");
 }
+// ---- cp.async (LDGSTS): global -> shared without register staging; BYTES = 8 or 16, both addresses BYTES-aligned ----------
+template <int BYTES> __device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src) {
+  static_assert(BYTES == 8 || BYTES == 16, "cp.async.ca supports 4, 8 and 16 bytes");
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {   // the issuing thread may read what its own cp.asyncs wrote
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2,
                                             uint64_t* bar) {
   asm volatile(

@@ -212,13 +212,11 @@ ED_DEVICE void half_body(const EpiArgs& A, int xg, int yr, uint8_t* smem_slots) 
       const int tid = threadIdx.y * blockDim.x + threadIdx.x;
       const int slot = (tid & ~31) | ((tid & 15) << 1) | ((tid >> 4) & 1);
       OT* mine = slots + slot * 4;
-      for (int ks = 0; ks < 2 * R1; ++ks) {
-        const OT* src = sample(ks * P.B + b) + c * plane + doff;
-        if constexpr (sizeof(OT) == 4)
-          *reinterpret_cast<float4*>(mine + ks * KS) = __ldg(reinterpret_cast<const float4*>(src));
-        else
-          *reinterpret_cast<uint2*>(mine + ks * KS) = __ldg(reinterpret_cast<const uint2*>(src));
-      }
+      // cp.async (LDGSTS): every vector straight from global into its slot, all 2*R1 in flight at once, no staging
+      // registers; a load-store-load-store loop would serialise the memory latency of every vector
+      for (int ks = 0; ks < 2 * R1; ++ks)
+        cp_async<4 * (int)sizeof(OT)>(mine + ks * KS, sample(ks * P.B + b) + c * plane + doff);
+      cp_async_wait_all();
       float lun[4], lco[4];                                      // scores of the owner at pixel (2r, 2c) = row 0, even column
 #pragma unroll
       for (int r = 0; r < 2; ++r)

@@ -101,6 +101,8 @@ static inline void emu_complete_tx(uint64_t* bar, uint64_t bytes) {
   const uint64_t left = (emu_bar(bar).fetch_sub(bytes) - bytes) & EMU_PENDING_MASK;
   if (left == 0) emu_bar(bar).fetch_add(1ull << 40);   // phase flip
 }
+template <int BYTES> static inline void cp_async(void* smem_dst, const void* gmem_src) { memcpy(smem_dst, gmem_src, BYTES); }
+static inline void cp_async_wait_all() {}
 static inline void tma_load_3d(void* smem_dst, const EmuTensorMap* m, int c0, int c1, int c2, uint64_t* bar) {
   uint8_t* dst = static_cast<uint8_t*>(smem_dst);
   for (int k = 0; k < m->b2; ++k)
