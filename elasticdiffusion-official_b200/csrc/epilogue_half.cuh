@@ -23,6 +23,9 @@
 #include "epilogue_staged.cuh"
 
 #define HALF_THREADS 128   // threads per CTA of the half kernels (the per-thread slot stride of the R1 > 1 kernel depends on it)
+#ifndef ED_HALF_MINB_MULTI
+#define ED_HALF_MINB_MULTI 4   // same for the R1 > 1 kernel
+#endif
 #ifndef ED_HALF_MINB
 #define ED_HALF_MINB 6   // resident 128-thread CTAs per SM the R1 == 1 kernel is compiled for (register cap 65536 / (128 * MINB))
 #endif
@@ -254,7 +257,7 @@ ED_DEVICE void half_body(const EpiArgs& A, int xg, int yr, uint8_t* smem_slots) 
 // The step's flags live in DEVICE memory (a captured launch is replayed with new parameters), so RRG / fp16 semantics are
 // CTA-uniform run-time branches into four specialised bodies rather than launch-time template arguments.
 template <typename OT, bool MULTI, bool PEER>
-__global__ void __launch_bounds__(HALF_THREADS, MULTI ? 4 : ED_HALF_MINB) wave_epilogue_half_kernel(const EpiArgs A) {
+__global__ void __launch_bounds__(HALF_THREADS, MULTI ? ED_HALF_MINB_MULTI : ED_HALF_MINB) wave_epilogue_half_kernel(const EpiArgs A) {
   ED_DYN_SMEM(smem_raw);
   const int xg = blockIdx.x * blockDim.x + threadIdx.x;   // group of 8 columns
   const int yr = blockIdx.y * blockDim.y + threadIdx.y;   // row pair = low-res row

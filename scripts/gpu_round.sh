@@ -25,6 +25,9 @@ for s in $STAGES; do
     minb8) ED_NVCC_FLAGS="-DED_HALF_MINB=8" python -c "import importlib; importlib.import_module('elasticdiffusion-official_b200').native.build(force=True)" && \
            timeout 240 python bench.py --roofline-only --roofline-cases 'ed_wave_epilogue+rrg(wave2:R1=1),ed_wave_epilogue(wave2:R1=1)' > gpurun_out/roofline_minb8.json 2> gpurun_out/roofline_minb8.err; rc=$?; \
            python -c "import importlib; importlib.import_module('elasticdiffusion-official_b200').native.build(force=True)" ;;
+    minbm) for m in 5 6; do ED_NVCC_FLAGS="-DED_HALF_MINB_MULTI=$m" python -c "import importlib; importlib.import_module('elasticdiffusion-official_b200').native.build(force=True)" && \
+           timeout 240 python bench.py --roofline-only --roofline-cases 'ed_wave_epilogue+rrg' > gpurun_out/roofline_minbm$m.json 2> gpurun_out/roofline_minbm$m.err; cat gpurun_out/roofline_minbm$m.json; done; rc=$?; \
+           python -c "import importlib; importlib.import_module('elasticdiffusion-official_b200').native.build(force=True)" ;;
     benchref) timeout 900 python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; rc=$? ;;
     probe) timeout 600 python scripts/probe_unet.py gpurun_out/probe_unet.json > gpurun_out/probe_unet.log 2>&1; rc=$? ;;
     launches) BENCH_GRAPHS=0 BENCH_CUPROF=1 timeout 420 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 5000 --csv \
@@ -33,6 +36,10 @@ for s in $STAGES; do
            scripts/check_multi_gpu.py > gpurun_out/multi_gpu_n${NGPU:-2}.log 2>&1; rc=$? ;;
     scale) for n in ${SCALE_NS:-"2 4 8"}; do timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 \
              --master-port 29544 bench.py --gpus $n --steps 8 --warmup 3 --no-extras > gpurun_out/bench_n$n.json 2> gpurun_out/bench_n$n.err; done; rc=$? ;;
+    scale4) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-8} --master-addr 127.0.0.1 --master-port 29555 \
+             bench.py --gpus ${NGPU:-8} --workload cfg4 --steps 8 --warmup 3 --no-extras > gpurun_out/bench_cfg4_n${NGPU:-8}.json 2> gpurun_out/bench_cfg4_n${NGPU:-8}.err; rc=$? ;;
+    scale5) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29566 \
+             bench.py --gpus 4 --workload cfg5 --steps 8 --warmup 3 --no-extras > gpurun_out/bench_cfg5_n4.json 2> gpurun_out/bench_cfg5_n4.err; rc=$? ;;
     smoke) timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; rc=$? ;;
     *) echo "unknown stage $s"; rc=99 ;;
   esac
@@ -43,6 +50,8 @@ for f in t_gpu t_kernels t_peer t_e2e; do [ -f gpurun_out/$f.log ] && tail -4 gp
 [ -f gpurun_out/bench_n1.json ] && head -c 1500 gpurun_out/bench_n1.json
 [ -f gpurun_out/bench.err ] && tail -5 gpurun_out/bench.err
 [ -f gpurun_out/bench_ref.json ] && head -c 600 gpurun_out/bench_ref.json
+for f in gpurun_out/bench_n*.json gpurun_out/bench_cfg*_n*.json; do [ -f $f ] && { echo "== $f"; tail -1 $f | head -c 400; echo; }; done
+for f in gpurun_out/multi_gpu_n*.log; do [ -f $f ] && tail -12 $f; done
 for f in bench_cfg5 bench_cfg4 bench_cfg2; do [ -f gpurun_out/$f.err ] && tail -3 gpurun_out/$f.err; done
 [ -f gpurun_out/roofline_minb8.json ] && cat gpurun_out/roofline_minb8.json
 true
