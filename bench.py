@@ -536,6 +536,10 @@ def parity_check(ed, unet, workload, device, world, rank, kw, n_steps=2, control
             if i + 1 == n_steps:
                 got["x"] = x.clone()
                 raise _Stop
+        for mod in (unet, controlnet):             # the checker runs the plain torch formulation of the same weights
+            if mod is not None and hasattr(mod, "set_ops"):
+                saved_ops = mod.ops
+                mod.set_ops(pkg().unet_ops.TorchOps)
         m = rp.Models(_NoAutocast(unet), syn.StubVAE().to(device), DDIMRestated(),
                       syn.StubTextEncoder(cross, pooled, device=device), sd, device, vb, projection_dim=pooled,
                       controlnet=_NoAutocast(controlnet) if controlnet is not None else None)
@@ -544,10 +548,13 @@ def parity_check(ed, unet, workload, device, world, rank, kw, n_steps=2, control
             rp.denoise(m, step_callback=cb, **{k: v for k, v in kw.items() if k != "progress"})
         except _Stop:
             pass
+        for mod in (unet, controlnet):
+            if mod is not None and hasattr(mod, "set_ops"):
+                mod.set_ops(saved_ops)
         mse = torch.mean((lat.float() - got["x"].float()) ** 2).item()
         out.update(latent_mse_vs_port=mse, latent_rms=float(got["x"].float().pow(2).mean().sqrt()),
                    ok=bool(mse <= 1e-3) and out.get("ranks_identical", True),
-                   checker="oracle/reference_port.denoise, eager on the same device, same bf16 UNet object")
+                   checker="oracle/reference_port.denoise, eager on the same device, same bf16 UNet weights with plain torch ops")
     if world > 1:
         dist.barrier()
     return out
@@ -621,6 +628,8 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=list(WORKLOADS))
     ap.add_argument("--no-extras", action="store_true", help="skip roofline / cpu_baseline / e2e legs (debug)")
     ap.add_argument("--no-decode", action="store_true", help="cfg4: skip the tiled-decode timing")
+    ap.add_argument("--unet-ops", default=os.environ.get("BENCH_UNET_OPS", "fused"), choices=["fused", "torch"],
+                    help="GEGLU / GroupNorm(+SiLU) inside the stand-in UNet: the library's fused kernels (unet_ops.py) or plain torch")
     ap.add_argument("--no-parity", action="store_true", help="skip the un-timed parity steps against the oracle port (debug)")
     ap.add_argument("--roofline-only", action="store_true", help="only the L2-exceeding kernel roofline table (debug / ncu)")
     ap.add_argument("--roofline-cases", default="", help="comma-separated kernel_rooflines case names (with --roofline-only)")
@@ -660,6 +669,15 @@ def main():
     ed.exchange = os.environ.get("BENCH_EXCHANGE", "p2p")              # multi-GPU: fused epilogue + NVLink peer reads
     if os.environ.get("BENCH_CL", "0") == "1":
         unet.to(memory_format=torch.channels_last)
+    # the UNet's GEGLU / GroupNorm(+SiLU) through the library's fused kernels (opt-in feature of the product);
+    # the reference legs and the parity checker always run the plain torch formulation of the same weights
+    fused_ops = P.unet_ops.FusedOps() if args.unet_ops == "fused" else None
+
+    def use_ops(fused):
+        for m in (unet, cn):
+            if m is not None:
+                m.set_ops(fused_ops if (fused and fused_ops is not None) else P.unet_ops.TorchOps)
+    use_ops(True)
     kw = dict(GEN, height=H, width=Wd, num_inference_steps=T, resampling_steps=R, progress=lambda it: it)
     if cn is not None:
         kw.update(condition_image=condition_image(args.workload, device), controlnet_conditioning_scale=COND_SCALE)
@@ -740,7 +758,16 @@ def main():
             # the half kernels (exact 1/2 ratio); re-noise launches: one latent per launch is small and L2-resident -> the
             # direct kernel, the TMA tile-staged kernel serves launches that fill the GPU
             "epilogue_kernels": {"direct": epi1[0] - epi0[0], "staged": epi1[1] - epi0[1], "half": epi1[2] - epi0[2]}}
+    line["config"]["unet_ops"] = ("fused ed_geglu + ed_groupnorm_silu inside the UNet (unet_ops.FusedOps): %s" % dict(fused_ops.calls)
+                                  if fused_ops is not None else "plain torch")
     if not args.no_extras:
+        if fused_ops is not None:       # A/B: the same run with the UNet's plain torch ops
+            use_ops(False)
+            ed._graphs = {}
+            sec_t, _, _ = timed_run(host_io=False)
+            use_ops(True)
+            ed._graphs = {}
+            line["unet_ops_ab"] = {"fused": value, "torch": K / sec_t, "unit": "denoise-steps/s"}
         sec2, _, d2h = timed_run(host_io=True)
         n_cells = (H // 16) * (Wd // 16)
         h2d = (R + 1) * n_cells + 2 * ctypes.sizeof(P.native.StepParams) + 2 * 2 * (77 * cross + (pooled or 0)) * 4 // (W_ + K)
@@ -772,6 +799,7 @@ def main():
         ed._graphs = {}
         torch.cuda.empty_cache()
         try:   # GPU-vs-GPU: the reference's own eager path on this B200 (the 10x target's denominator), two dtypes
+            use_ops(False)
             same = reference_gpu_eager_same_dtype(args.workload, device, unet, controlnet=cn)
             del unet, cn
             ed.unet = ed.controlnet = None

@@ -7,7 +7,7 @@ top-level drop-in module `elastic_diffusion` (same module name as the reference'
 from .pipeline import (ConstScheduler, CosineScheduler, ElasticDiffusion, LinearScheduler, RngLedger, TimeIt,
                        timelog)
 from .ddim import DDIMSchedule
-from . import controlnet, geometry, native
+from . import controlnet, geometry, native, unet_ops
 
 __all__ = ["ElasticDiffusion", "CosineScheduler", "LinearScheduler", "ConstScheduler", "TimeIt", "timelog",
-           "DDIMSchedule", "RngLedger", "controlnet", "geometry", "native"]
+           "DDIMSchedule", "RngLedger", "controlnet", "geometry", "native", "unet_ops"]

@@ -13,7 +13,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libelastic_b200.so")
-SOURCES = ["abi.cu", "gather.cu", "epilogue.cu", "tiles.cu"]
+SOURCES = ["abi.cu", "gather.cu", "epilogue.cu", "tiles.cu", "unet_ops.cu"]
 ED_MAX_RENOISE = 1000
 ED_F32, ED_F16, ED_BF16 = 0, 1, 2
 FLAG_RENOISE, FLAG_RRG, FLAG_FP16_SEM = 1, 2, 4
@@ -76,6 +76,10 @@ EXPORTS = {
     "ed_tile_gather": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                  C.c_int, C.c_void_p, C.c_void_p]),
     "ed_tile_blend": (C.c_int, [C.POINTER(Tiles), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "ed_geglu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
+    "ed_groupnorm_split": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ed_groupnorm_silu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_float, C.c_int, C.c_int, C.c_void_p]),
     "ed_tile_blend_peer": (C.c_int, [C.POINTER(Tiles), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
 }
 

@@ -245,6 +245,20 @@ int ed_tile_blend(const ed_tiles_t* tiles, const void* patches, int patch_dtype,
 int ed_tile_blend_peer(const ed_tiles_t* tiles, const void* const* d_peer_patches, int world, int per, int patch_dtype,
                        float* image, void* stream);
 
+/* ---- opt-in: fused element-wise / normalisation ops INSIDE the UNet forward (unet_ops.py) -----------
+ * Not part of the reference's loop (its UNet is diffusers'); they replace the two largest non-GEMM costs of the SDXL-shaped
+ * UNet forward that every wave of the loop spends its time in.
+ * ed_geglu: x (M, 2N) contiguous of `dtype`, out (M, N) = x[:, :N] * gelu(x[:, N:]) (erf form) with the intermediate rounding
+ *           of gelu to `dtype` that torch's two kernels apply -> bit-identical to `a, g = x.chunk(2, -1); a * F.gelu(g)`.
+ *           N % 8 == 0, 16-byte aligned pointers (else ED_ERR_UNSUPPORTED). */
+int ed_geglu(const void* x, void* out, int64_t M, int N, int dtype, void* stream);
+/* ed_groupnorm_silu: out = [silu](group_norm(x, G, gamma, beta, eps)) for contiguous NCHW x (N, C, HW) of `dtype` (gamma /
+ *           beta of the same dtype or NULL).  `workspace`: N*G*ed_groupnorm_split(N,C,HW,G)*2 floats.  Two launches: split
+ *           statistics (N*G*S CTAs, shifted sums) + apply.  HW % 8 == 0, 16-byte aligned pointers. */
+int ed_groupnorm_split(int N, int C, int HW, int G);
+int ed_groupnorm_silu(const void* x, const void* gamma, const void* beta, void* out, float* workspace, int N, int C, int HW,
+                      int G, float eps, int silu, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

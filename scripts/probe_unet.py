@@ -20,7 +20,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import standins as syn  # noqa: E402
 
 dev = torch.device("cuda")
-OUT = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/probe_unet.json"
+OUT = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("--") else "gpurun_out/probe_unet.json"
 res = {}
 
 
@@ -80,6 +80,20 @@ def save():
 
 unet = syn.StandInUNet("XL1.0", device=dev, dtype=torch.bfloat16).eval()
 NS = (1, 2, 3, 4, 5, 6, 8, 10, 20)
+if "--fused-sweep" in sys.argv:      # t(n) with the library's fused GEGLU / GroupNorm(+SiLU) kernels inside the UNet, then plain
+    import importlib
+    ops = importlib.import_module("elasticdiffusion-official_b200").unet_ops
+    OUT = "gpurun_out/probe_unet_fused.json"
+    fo = ops.FusedOps()
+    unet.set_ops(fo)
+    res["sweep_fused"] = sweep(unet, NS)
+    res["fused_calls"] = dict(fo.calls)
+    print("sweep_fused", res["sweep_fused"], flush=True)
+    unet.set_ops(ops.TorchOps)
+    res["sweep_torch"] = sweep(unet, (1, 3, 6, 20))
+    print("sweep_torch", res["sweep_torch"], flush=True)
+    save()
+    sys.exit(0)
 res["sweep"] = sweep(unet, NS)
 print("sweep", res["sweep"], flush=True)
 save()

@@ -216,7 +216,28 @@ class StubTextEncoder:
 # SD / SDXL-shaped random-weight UNet for throughput runs
 # --------------------------------------------------------------------------------------------------------------
 
+class _PlainOps:
+    """The element-wise / normalisation patterns of the UNet as plain PyTorch (what diffusers' modules run).  A UNet instance
+    can be given another implementation of this interface through `StandInUNet.set_ops` - e.g. the product's fused kernels
+    (`elasticdiffusion-official_b200/unet_ops.py`); the stand-ins themselves never import the product."""
+
+    @staticmethod
+    def geglu(x):
+        a, g = x.chunk(2, dim=-1)
+        return a * F.gelu(g)
+
+    @staticmethod
+    def group_norm(gn, x):
+        return gn(x)
+
+    @staticmethod
+    def group_norm_silu(gn, x):
+        return F.silu(gn(x))
+
+
 class _ResBlock(nn.Module):
+    ops = _PlainOps
+
     def __init__(self, cin, cout, temb):
         super().__init__()
         self.n1 = nn.GroupNorm(32, cin)
@@ -227,9 +248,9 @@ class _ResBlock(nn.Module):
         self.skip = nn.Conv2d(cin, cout, 1) if cin != cout else None
 
     def forward(self, x, emb):
-        h = self.c1(F.silu(self.n1(x)))
+        h = self.c1(self.ops.group_norm_silu(self.n1, x))
         h = h + self.t(F.silu(emb))[:, :, None, None]
-        h = self.c2(F.silu(self.n2(h)))
+        h = self.c2(self.ops.group_norm_silu(self.n2, h))
         return h + (x if self.skip is None else self.skip(x))
 
 
@@ -252,6 +273,8 @@ class _Attn(nn.Module):
 
 
 class _TBlock(nn.Module):
+    ops = _PlainOps
+
     def __init__(self, dim, ctx_dim, head_dim):
         super().__init__()
         self.n1, self.n2, self.n3 = nn.LayerNorm(dim), nn.LayerNorm(dim), nn.LayerNorm(dim)
@@ -264,11 +287,12 @@ class _TBlock(nn.Module):
         y = self.n1(x)
         x = x + self.a1(y, y)
         x = x + self.a2(self.n2(x), ctx)
-        a, g = self.ff1(self.n3(x)).chunk(2, dim=-1)
-        return x + self.ff2(a * F.gelu(g))
+        return x + self.ff2(self.ops.geglu(self.ff1(self.n3(x))))
 
 
 class _Transformer2D(nn.Module):
+    ops = _PlainOps
+
     def __init__(self, dim, ctx_dim, head_dim, depth):
         super().__init__()
         self.norm = nn.GroupNorm(32, dim)
@@ -278,7 +302,7 @@ class _Transformer2D(nn.Module):
 
     def forward(self, x, ctx):
         b, c, h, w = x.shape
-        y = self.pin(self.norm(x).flatten(2).transpose(1, 2))
+        y = self.pin(self.ops.group_norm(self.norm, x).flatten(2).transpose(1, 2))
         for blk in self.blocks:
             y = blk(y, ctx)
         y = self.pout(y).transpose(1, 2).reshape(b, c, h, w)
@@ -321,6 +345,15 @@ class StandInUNet(nn.Module):
             self._build(preset, layers_per_block, head_dim, seed)
 
     ENCODER_ONLY = False    # StandInControlNet: conv_in + down path + mid block only
+    ops = _PlainOps
+
+    def set_ops(self, ops):
+        """Route GEGLU / GroupNorm(+SiLU) of every block through `ops` (interface of `_PlainOps`)."""
+        self.ops = ops
+        for m in self.modules():
+            if isinstance(m, (_ResBlock, _TBlock, _Transformer2D)):
+                m.ops = ops
+        return self
 
     def _build(self, preset, layers_per_block, head_dim, seed):
         p = self.PRESETS[preset]
@@ -412,7 +445,7 @@ class StandInUNet(nn.Module):
             h = h if isinstance(attn, nn.Identity) else attn(h, ctx)
             if upc is not None:
                 h = upc(F.interpolate(h, scale_factor=2.0, mode="nearest"))
-        return {"sample": self.conv_out(F.silu(self.norm_out(h)))}
+        return {"sample": self.conv_out(self.ops.group_norm_silu(self.norm_out, h))}
 
 
 class StandInControlNet(StandInUNet):

@@ -283,3 +283,28 @@ def test_strip_precompute_is_rng_neutral_and_batched(name):
     assert led.precompute_strips(ed.scheduler.timesteps) >= 1 and len(led.strip_cache) == n_strips
     assert torch.equal(torch.rand(3), want)
     assert (__import__("numpy").random.get_state()[1] == np_state).all()
+
+
+def test_fused_unet_ops_fall_back_to_torch_outside_their_domain():
+    """CPU tensors (no CUDA here): FusedOps must return exactly what TorchOps returns and count the fall-backs; the stand-in
+    UNet routes GEGLU / GroupNorm(+SiLU) through whatever ops object it is given."""
+    import importlib
+    import standins
+    ops_mod = importlib.import_module(PKG.__name__ + ".unet_ops")
+    fo = ops_mod.FusedOps()
+    x = torch.randn(3, 7, 32)
+    assert torch.equal(fo.geglu(x), ops_mod.TorchOps.geglu(x))
+    gn = torch.nn.GroupNorm(4, 8)
+    y = torch.randn(2, 8, 4, 4)
+    assert torch.equal(fo.group_norm_silu(gn, y), torch.nn.functional.silu(gn(y))) and torch.equal(fo.group_norm(gn, y), gn(y))
+    assert fo.calls == {"geglu": 0, "group_norm": 0, "fallback": 3}
+    unet = standins.StandInUNet("tiny-xl").eval()
+    n = 1
+    args = (torch.randn(n, 4, 32, 32), torch.tensor(981))
+    kw = dict(encoder_hidden_states=torch.randn(n, 77, 64),
+              added_cond_kwargs={"text_embeds": torch.randn(n, 32), "time_ids": torch.tensor([[256., 256, 0, 0, 256, 256]])})
+    with torch.no_grad():
+        a = unet(*args, **kw)["sample"]
+        unet.set_ops(fo)
+        b = unet(*args, **kw)["sample"]
+    assert torch.equal(a, b) and fo.calls["fallback"] > 10
