@@ -24,7 +24,7 @@
 
 #define HALF_THREADS 128   // threads per CTA of the half kernels (the per-thread slot stride of the R1 > 1 kernel depends on it)
 #ifndef ED_HALF_MINB_MULTI
-#define ED_HALF_MINB_MULTI 4   // same for the R1 > 1 kernel
+#define ED_HALF_MINB_MULTI 5   // same for the R1 > 1 kernel (measured: 4 -> 0.52, 5 -> 0.56, 6 -> 0.54 of the HBM roofline)
 #endif
 #ifndef ED_HALF_MINB
 #define ED_HALF_MINB 6   // resident 128-thread CTAs per SM the R1 == 1 kernel is compiled for (register cap 65536 / (128 * MINB))
