@@ -758,7 +758,7 @@ def main():
             # the half kernels (exact 1/2 ratio); re-noise launches: one latent per launch is small and L2-resident -> the
             # direct kernel, the TMA tile-staged kernel serves launches that fill the GPU
             "epilogue_kernels": {"direct": epi1[0] - epi0[0], "staged": epi1[1] - epi0[1], "half": epi1[2] - epi0[2]}}
-    line["config"]["unet_ops"] = ("fused ed_geglu + ed_groupnorm_silu inside the UNet (unet_ops.FusedOps): %s" % dict(fused_ops.calls)
+    line["config"]["unet_ops"] = ("fused ed_geglu / ed_groupnorm_silu / ed_layernorm / ed_bias_add inside the UNet (unet_ops.FusedOps): %s" % dict(fused_ops.calls)
                                   if fused_ops is not None else "plain torch")
     if not args.no_extras:
         if fused_ops is not None:       # A/B: the same run with the UNet's plain torch ops

@@ -165,9 +165,158 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, 
   }
 }
 
+// ---- conv epilogue: y += bias[c] (+ per_nc[n, c]) (+ residual), each step rounded to the tensor dtype like the separate torch
+// ops (cuDNN conv output -> add_(bias) -> + time-embedding broadcast -> + residual): grid (N*C, chunks of the HW plane) --------
+template <typename T>
+__global__ void __launch_bounds__(256) bias_add_kernel(T* __restrict__ y, const T* __restrict__ bias, const T* __restrict__ per_nc,
+                                                       const T* __restrict__ residual, int C, int HW) {
+  const long long nc = blockIdx.x;
+  const int c = (int)(nc % C);
+  const float b = bias ? to_f32<T>(__ldg(bias + c)) : 0.f;
+  const float e = per_nc ? to_f32<T>(__ldg(per_nc + nc)) : 0.f;
+  T* dst = y + nc * HW;
+  const T* res = residual ? residual + nc * HW : nullptr;
+  const int v8 = HW / 8;
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < v8; i += gridDim.y * blockDim.x) {
+    Pack8<T> p, r;
+    p.load(dst + (long long)i * 8);
+    float v[8], rv[8];
+    p.get(v);
+    if (res) {
+      r.load(res + (long long)i * 8);
+      r.get(rv);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float t = v[k];
+      if (bias) t = round_to<T>(__fadd_rn(t, b));
+      if (per_nc) t = round_to<T>(__fadd_rn(t, e));
+      if (res) t = __fadd_rn(t, rv[k]);
+      v[k] = t;
+    }
+    store8<T>(dst + (long long)i * 8, v);
+  }
+}
+
+// ---- LayerNorm over the last dimension: one warp per row, the row lives in registers (two-pass mean / variance) -------------
+// D % 8 == 0 and D <= 32 * 8 * VPL.  out = (x - mean) * rstd * gamma + beta in float, written as dtype (torch's formula).
+template <typename T, int VPL>
+__global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x, const T* __restrict__ gamma, const T* __restrict__ beta,
+                                                        T* __restrict__ out, long long M, int D, float eps) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const int nv = D / 8;                                           // 8-element vectors per row
+  const T* src = x + row * D;
+  float v[VPL][8];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const int vi = lane + 32 * j;
+    if (vi < nv) {
+      Pack8<T> p;
+      p.load(src + vi * 8);
+      p.get(v[j]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += v[j][k];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < VPL; ++j)
+    if (lane + 32 * j < nv) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float d = v[j][k] - mean;
+        q = fmaf(d, d, q);
+      }
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)D + eps);
+  T* dst = out + row * D;
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const int vi = lane + 32 * j;
+    if (vi < nv) {
+      float g[8], b[8];
+      if (gamma) {
+        Pack8<T> pg;
+        pg.load(gamma + vi * 8);
+        pg.get(g);
+      }
+      if (beta) {
+        Pack8<T> pb;
+        pb.load(beta + vi * 8);
+        pb.get(b);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float y = (v[j][k] - mean) * rstd;
+        if (gamma) y *= g[k];
+        if (beta) y += b[k];
+        v[j][k] = y;
+      }
+      store8<T>(dst + vi * 8, v[j]);
+    }
+  }
+}
+
 }  // namespace ed
 
 using namespace ed;
+
+extern "C" int ed_bias_add(void* y, const void* bias, const void* per_nc, const void* residual, int N, int C, int HW, int dtype,
+                           void* stream_) {
+  if (!y || N <= 0 || C <= 0 || HW <= 0) return ED_ERR_INVALID;
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (HW % 8 || !al(y) || (residual && !al(residual))) return ED_ERR_UNSUPPORTED;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int chunks = (HW / 8 + 255) / 256;
+  if (chunks > 64) chunks = 64;
+  const dim3 g((unsigned)((long long)N * C), (unsigned)chunks);
+  switch (dtype) {
+    case ED_F32: bias_add_kernel<float><<<g, 256, 0, stream>>>((float*)y, (const float*)bias, (const float*)per_nc, (const float*)residual, C, HW); break;
+    case ED_F16: bias_add_kernel<__half><<<g, 256, 0, stream>>>((__half*)y, (const __half*)bias, (const __half*)per_nc, (const __half*)residual, C, HW); break;
+    case ED_BF16: bias_add_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>((__nv_bfloat16*)y, (const __nv_bfloat16*)bias, (const __nv_bfloat16*)per_nc, (const __nv_bfloat16*)residual, C, HW); break;
+    default: return ED_ERR_INVALID;
+  }
+  ED_LAUNCH_CHECK();
+  return ED_OK;
+}
+
+template <typename T>
+static int launch_layernorm(const void* x, const void* gamma, const void* beta, void* out, long long M, int D, float eps,
+                            cudaStream_t stream) {
+  const int nv = D / 8;
+  const unsigned grid = (unsigned)((M + 7) / 8);
+  const T *xx = (const T*)x, *g = (const T*)gamma, *b = (const T*)beta;
+  if (nv <= 32) layernorm_kernel<T, 1><<<grid, 256, 0, stream>>>(xx, g, b, (T*)out, M, D, eps);
+  else if (nv <= 64) layernorm_kernel<T, 2><<<grid, 256, 0, stream>>>(xx, g, b, (T*)out, M, D, eps);
+  else if (nv <= 96) layernorm_kernel<T, 3><<<grid, 256, 0, stream>>>(xx, g, b, (T*)out, M, D, eps);
+  else if (nv <= 160) layernorm_kernel<T, 5><<<grid, 256, 0, stream>>>(xx, g, b, (T*)out, M, D, eps);
+  else if (nv <= 256) layernorm_kernel<T, 8><<<grid, 256, 0, stream>>>(xx, g, b, (T*)out, M, D, eps);
+  else return ED_ERR_UNSUPPORTED;
+  ED_LAUNCH_CHECK();
+  return ED_OK;
+}
+
+extern "C" int ed_layernorm(const void* x, const void* gamma, const void* beta, void* out, int64_t M, int D, float eps, int dtype,
+                            void* stream_) {
+  if (!x || !out || M <= 0 || D <= 0) return ED_ERR_INVALID;
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (D % 8 || !al(x) || !al(out) || (gamma && !al(gamma)) || (beta && !al(beta))) return ED_ERR_UNSUPPORTED;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  switch (dtype) {
+    case ED_F32: return launch_layernorm<float>(x, gamma, beta, out, M, D, eps, stream);
+    case ED_F16: return launch_layernorm<__half>(x, gamma, beta, out, M, D, eps, stream);
+    case ED_BF16: return launch_layernorm<__nv_bfloat16>(x, gamma, beta, out, M, D, eps, stream);
+    default: return ED_ERR_INVALID;
+  }
+}
 
 extern "C" int ed_geglu(const void* x, void* out, int64_t M, int N, int dtype, void* stream_) {
   if (!x || !out || M <= 0 || N <= 0) return ED_ERR_INVALID;

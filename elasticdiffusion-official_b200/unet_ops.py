@@ -9,6 +9,8 @@ call sites are `GEGLU.forward` and `ResnetBlock2D.forward` / `Transformer2DModel
     ops.geglu(x)                      # x = proj(hidden) of shape (..., 2N)  ->  x[..., :N] * gelu(x[..., N:])
     ops.group_norm(gn_module, x)      # nn.GroupNorm forward
     ops.group_norm_silu(gn_module, x) # silu(group_norm(x))
+    ops.layer_norm(ln_module, x)      # nn.LayerNorm forward over the last dimension
+    ops.conv_add(conv, x, per_nc=None, residual=None)   # conv(x) [+ per_nc[:, :, None, None]] [+ residual]
 
 `TorchOps` is the plain PyTorch formulation (what the reference's models run); `FusedOps` calls the kernels and falls back
 to `TorchOps` per call for shapes outside the kernels' domain (non-contiguous, HW % 8 != 0, CPU tensors, autograd).
@@ -35,12 +37,25 @@ class TorchOps:
     def group_norm_silu(gn, x):
         return F.silu(gn(x))
 
+    @staticmethod
+    def layer_norm(ln, x):
+        return ln(x)
+
+    @staticmethod
+    def conv_add(conv, x, per_nc=None, residual=None):
+        h = conv(x)
+        if per_nc is not None:
+            h = h + per_nc[:, :, None, None]
+        if residual is not None:
+            h = h + residual
+        return h
+
 
 class FusedOps:
     """Kernels of csrc/unet_ops.cu; `calls` counts how many went to the library / to the torch fall-back."""
 
     def __init__(self):
-        self.calls = {"geglu": 0, "group_norm": 0, "fallback": 0}
+        self.calls = {"geglu": 0, "group_norm": 0, "layer_norm": 0, "conv_add": 0, "fallback": 0}
         self._ws = {}
 
     def _ok(self, x):
@@ -80,6 +95,46 @@ class FusedOps:
                                          native.stream_handle()), "ed_groupnorm_silu")
         self.calls["group_norm"] += 1
         return out
+
+    def layer_norm(self, ln, x):
+        D = x.shape[-1]
+        w, b = ln.weight, ln.bias
+        if (not self._ok(x) or len(ln.normalized_shape) != 1 or ln.normalized_shape[0] != D or D % 8 or D > 2048 or
+                (w is not None and w.dtype != x.dtype) or (b is not None and b.dtype != x.dtype)):
+            self.calls["fallback"] += 1
+            return ln(x)
+        out = torch.empty_like(x)
+        native.check(native.lib().ed_layernorm(native.ptr(x), native.ptr(w), native.ptr(b), native.ptr(out), x.numel() // D, D,
+                                               float(ln.eps), native.dtype_code(x.dtype), native.stream_handle()), "ed_layernorm")
+        self.calls["layer_norm"] += 1
+        return out
+
+    def conv_add(self, conv, x, per_nc=None, residual=None):
+        """cuDNN conv WITHOUT its bias, then one vectorised in-place pass for bias + time-embedding + residual (torch runs the
+        bias and the time-embedding as two unvectorised broadcast adds); bit-identical to the separate ops."""
+        if (not self._ok(x) or x.dim() != 4 or not isinstance(conv, torch.nn.Conv2d) or conv.padding_mode != "zeros" or
+                (conv.bias is not None and conv.bias.dtype != x.dtype)):
+            self.calls["fallback"] += 1
+            return TorchOps.conv_add(conv, x, per_nc, residual)
+        y = F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+        N, C = y.shape[0], y.shape[1]
+        HW = y.shape[2] * y.shape[3]
+        ok = y.is_contiguous() and HW % 8 == 0 and \
+            (per_nc is None or (per_nc.is_contiguous() and per_nc.dtype == y.dtype and tuple(per_nc.shape) == (N, C))) and \
+            (residual is None or (residual.is_contiguous() and residual.dtype == y.dtype and residual.shape == y.shape))
+        if not ok:
+            self.calls["fallback"] += 1
+            if conv.bias is not None:
+                y = y + conv.bias[None, :, None, None]
+            if per_nc is not None:
+                y = y + per_nc[:, :, None, None]
+            return y if residual is None else y + residual
+        if conv.bias is None and per_nc is None and residual is None:
+            return y
+        native.check(native.lib().ed_bias_add(native.ptr(y), native.ptr(conv.bias), native.ptr(per_nc), native.ptr(residual), N, C, HW,
+                                              native.dtype_code(y.dtype), native.stream_handle()), "ed_bias_add")
+        self.calls["conv_add"] += 1
+        return y
 
     def group_norm(self, gn, x):
         return self._gn(gn, x, False)

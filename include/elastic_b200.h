@@ -255,6 +255,13 @@ int ed_geglu(const void* x, void* out, int64_t M, int N, int dtype, void* stream
 /* ed_groupnorm_silu: out = [silu](group_norm(x, G, gamma, beta, eps)) for contiguous NCHW x (N, C, HW) of `dtype` (gamma /
  *           beta of the same dtype or NULL).  `workspace`: N*G*ed_groupnorm_split(N,C,HW,G)*2 floats.  Two launches: split
  *           statistics (N*G*S CTAs, shifted sums) + apply.  HW % 8 == 0, 16-byte aligned pointers. */
+/* ed_bias_add: conv epilogue in place on contiguous NCHW y (N, C, HW): y += bias[c] (+ per_nc[n*C + c]) (+ residual[n, c, :]), each
+ *           step rounded to `dtype` like the separate torch ops (cuDNN conv -> add_(bias) -> + time-embedding -> + residual):
+ *           bit-identical, one vectorised pass instead of two or three unvectorised broadcast adds.  Any of the three may be NULL. */
+int ed_bias_add(void* y, const void* bias, const void* per_nc, const void* residual, int N, int C, int HW, int dtype, void* stream);
+/* ed_layernorm: LayerNorm over the last dimension of contiguous x (M, D): one warp per row, the row in registers, two-pass
+ *           statistics.  D % 8 == 0, D <= 2048, 16-byte aligned pointers; gamma / beta of the same dtype or NULL. */
+int ed_layernorm(const void* x, const void* gamma, const void* beta, void* out, int64_t M, int D, float eps, int dtype, void* stream);
 int ed_groupnorm_split(int N, int C, int HW, int G);
 int ed_groupnorm_silu(const void* x, const void* gamma, const void* beta, void* out, float* workspace, int N, int C, int HW,
                       int G, float eps, int silu, int dtype, void* stream);

@@ -234,6 +234,20 @@ class _PlainOps:
     def group_norm_silu(gn, x):
         return F.silu(gn(x))
 
+    @staticmethod
+    def layer_norm(ln, x):
+        return ln(x)
+
+    @staticmethod
+    def conv_add(conv, x, per_nc=None, residual=None):
+        """conv(x) [+ per_nc[:, :, None, None]] [+ residual] - a ResNet block's conv with its time-embedding / skip adds"""
+        h = conv(x)
+        if per_nc is not None:
+            h = h + per_nc[:, :, None, None]
+        if residual is not None:
+            h = h + residual
+        return h
+
 
 class _ResBlock(nn.Module):
     ops = _PlainOps
@@ -248,10 +262,9 @@ class _ResBlock(nn.Module):
         self.skip = nn.Conv2d(cin, cout, 1) if cin != cout else None
 
     def forward(self, x, emb):
-        h = self.c1(self.ops.group_norm_silu(self.n1, x))
-        h = h + self.t(F.silu(emb))[:, :, None, None]
-        h = self.c2(self.ops.group_norm_silu(self.n2, h))
-        return h + (x if self.skip is None else self.skip(x))
+        o = self.ops
+        h = o.conv_add(self.c1, o.group_norm_silu(self.n1, x), per_nc=self.t(F.silu(emb)))
+        return o.conv_add(self.c2, o.group_norm_silu(self.n2, h), residual=x if self.skip is None else o.conv_add(self.skip, x))
 
 
 class _Attn(nn.Module):
@@ -284,10 +297,11 @@ class _TBlock(nn.Module):
         self.ff2 = nn.Linear(dim * 4, dim)
 
     def forward(self, x, ctx):
-        y = self.n1(x)
+        o = self.ops
+        y = o.layer_norm(self.n1, x)
         x = x + self.a1(y, y)
-        x = x + self.a2(self.n2(x), ctx)
-        return x + self.ff2(self.ops.geglu(self.ff1(self.n3(x))))
+        x = x + self.a2(o.layer_norm(self.n2, x), ctx)
+        return x + self.ff2(o.geglu(self.ff1(o.layer_norm(self.n3, x))))
 
 
 class _Transformer2D(nn.Module):
@@ -422,7 +436,7 @@ class StandInUNet(nn.Module):
         skips = [h]
         for mods in self.down:
             if mods[1] is None:
-                h = mods[0](h)
+                h = self.ops.conv_add(mods[0], h)
             else:
                 h = mods[0](h, emb)
                 h = h if isinstance(mods[1], nn.Identity) else mods[1](h, ctx)
@@ -433,7 +447,7 @@ class StandInUNet(nn.Module):
     def forward(self, x, t, encoder_hidden_states=None, added_cond_kwargs=None, down_block_additional_residuals=None,
                 mid_block_additional_residual=None, **kw):
         emb, ctx, dt = self._embed(x, t, encoder_hidden_states, added_cond_kwargs)
-        skips, h = self._encode(self.conv_in(x.to(dt)), emb, ctx)
+        skips, h = self._encode(self.ops.conv_add(self.conv_in, x.to(dt)), emb, ctx)
         # ControlNet residuals as diffusers' UNet2DConditionModel applies them (reference elastic_diffusion_w_controlnet.py
         # :493-496 passes them through): one per skip connection + one for the mid block
         if down_block_additional_residuals is not None:
@@ -444,8 +458,8 @@ class StandInUNet(nn.Module):
             h = res(torch.cat([h, skips.pop()], dim=1), emb)
             h = h if isinstance(attn, nn.Identity) else attn(h, ctx)
             if upc is not None:
-                h = upc(F.interpolate(h, scale_factor=2.0, mode="nearest"))
-        return {"sample": self.conv_out(self.ops.group_norm_silu(self.norm_out, h))}
+                h = self.ops.conv_add(upc, F.interpolate(h, scale_factor=2.0, mode="nearest"))
+        return {"sample": self.ops.conv_add(self.conv_out, self.ops.group_norm_silu(self.norm_out, h))}
 
 
 class StandInControlNet(StandInUNet):

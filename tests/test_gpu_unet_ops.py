@@ -45,6 +45,45 @@ def test_groupnorm_silu_matches_torch(dtype, tol, N, C, H, W, silu):
     assert err_mine <= max(2 * err_torch, tol * scale), (err_mine, err_torch, scale)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize("N,Cin,Cout,H,k,stride", [(2, 320, 320, 64, 3, 1), (1, 640, 1280, 32, 3, 1), (3, 960, 640, 32, 1, 1),
+                                                   (2, 320, 320, 64, 3, 2), (1, 4, 320, 128, 3, 1)])
+def test_conv_add_is_bit_identical_to_the_separate_torch_ops(dtype, N, Cin, Cout, H, k, stride):
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(3)
+    conv = torch.nn.Conv2d(Cin, Cout, k, stride=stride, padding=k // 2).to("cuda", dtype)
+    x = torch.randn(N, Cin, H, H, device="cuda", generator=g).to(dtype)
+    Ho = H // stride
+    temb = torch.randn(N, Cout, device="cuda", generator=g).to(dtype)
+    res = torch.randn(N, Cout, Ho, Ho, device="cuda", generator=g).to(dtype)
+    fo = ops_mod.FusedOps()
+    with torch.no_grad():
+        for per_nc, residual in ((None, None), (temb, None), (None, res), (temb, res)):
+            got = fo.conv_add(conv, x, per_nc=per_nc, residual=residual)
+            want = ops_mod.TorchOps.conv_add(conv, x, per_nc=per_nc, residual=residual)
+            assert torch.equal(got, want), (per_nc is not None, residual is not None, (got.float() - want.float()).abs().max().item())
+    assert fo.calls["conv_add"] == 4 and fo.calls["fallback"] == 0
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, 2 ** -7), (torch.float16, 2 ** -10), (torch.float32, 2e-6)])
+@pytest.mark.parametrize("shape", [(2, 4096, 640), (3, 1024, 1280), (5, 77, 2048), (7, 64), (1, 9, 1024)])
+def test_layernorm_matches_torch(dtype, tol, shape):
+    g = torch.Generator(device="cuda").manual_seed(4)
+    D = shape[-1]
+    x = (torch.randn(shape, device="cuda", generator=g) * 2.0 + 0.3).to(dtype)
+    ln = torch.nn.LayerNorm(D).to("cuda", dtype)
+    with torch.no_grad():
+        ln.weight.copy_(torch.randn(D, device="cuda", generator=g) * 0.3 + 1)
+        ln.bias.copy_(torch.randn(D, device="cuda", generator=g) * 0.2)
+        fo = ops_mod.FusedOps()
+        got = fo.layer_norm(ln, x)
+        want64 = F.layer_norm(x.double(), (D,), ln.weight.double(), ln.bias.double(), ln.eps)
+        torch_out = ln(x)
+    assert fo.calls["layer_norm"] == 1
+    err_mine, err_torch = (got.double() - want64).abs().max().item(), (torch_out.double() - want64).abs().max().item()
+    assert err_mine <= max(2 * err_torch, tol * want64.abs().max().item()), (err_mine, err_torch)
+
+
 def test_large_offset_groups_do_not_cancel():
     """|mean| >> std: the shifted sums keep the variance (a naive E[x^2] - mean^2 in fp32 would lose it)."""
     x = (torch.randn(2, 64, 32, 32, device="cuda") * 0.01 + 300.0)
@@ -69,7 +108,7 @@ def test_standin_unet_with_fused_ops_matches_plain_ops_and_captures_in_a_cuda_gr
         fo = ops_mod.FusedOps()
         unet.set_ops(fo)
         fused = unet(x, t, encoder_hidden_states=ehs, **kw)["sample"].float()
-        assert fo.calls["geglu"] > 0 and fo.calls["group_norm"] > 0 and fo.calls["fallback"] == 0, fo.calls
+        assert min(fo.calls[k] for k in ("geglu", "group_norm", "layer_norm", "conv_add")) > 0 and fo.calls["fallback"] == 0, fo.calls
         rel = (fused - plain).pow(2).mean().sqrt().item() / plain.pow(2).mean().sqrt().item()
         assert rel < 2e-2, rel                       # bf16 network: GroupNorm statistics differ in the last bits
         s = torch.cuda.Stream()

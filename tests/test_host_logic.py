@@ -297,7 +297,11 @@ def test_fused_unet_ops_fall_back_to_torch_outside_their_domain():
     gn = torch.nn.GroupNorm(4, 8)
     y = torch.randn(2, 8, 4, 4)
     assert torch.equal(fo.group_norm_silu(gn, y), torch.nn.functional.silu(gn(y))) and torch.equal(fo.group_norm(gn, y), gn(y))
-    assert fo.calls == {"geglu": 0, "group_norm": 0, "fallback": 3}
+    ln = torch.nn.LayerNorm(32)
+    conv = torch.nn.Conv2d(8, 8, 3, padding=1)
+    assert torch.equal(fo.layer_norm(ln, x), ln(x))
+    assert torch.equal(fo.conv_add(conv, y, per_nc=torch.ones(2, 8), residual=y), conv(y) + 1 + y)
+    assert fo.calls == {"geglu": 0, "group_norm": 0, "layer_norm": 0, "conv_add": 0, "fallback": 5}
     unet = standins.StandInUNet("tiny-xl").eval()
     n = 1
     args = (torch.randn(n, 4, 32, 32), torch.tensor(981))
