@@ -160,7 +160,7 @@ def needed_global_elements(geo, R1, idx, owner, rrg):
     return int(torch.unique(torch.cat(keys)).numel())
 
 
-def kernel_rooflines(device, B=96, out_dtype=torch.bfloat16, iters=10, warm=3, only=None, ab=True):
+def kernel_rooflines(device, B=96, out_dtype=torch.bfloat16, iters=30, warm=3, only=None, ab=True):
     """Times every hot-path kernel of libelastic_b200 on a batch of B SDXL 1024x2048 latents (working sets of
     0.1-1.3 GiB, all larger than the 126 MB L2) and returns algorithmic GB/s per kernel.  Algorithmic bytes = every
     distinct input element the op needs, read once, + every output element, written once.  `ab`: also time the
@@ -633,7 +633,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the un-timed parity steps against the oracle port (debug)")
     ap.add_argument("--roofline-only", action="store_true", help="only the L2-exceeding kernel roofline table (debug / ncu)")
     ap.add_argument("--roofline-cases", default="", help="comma-separated kernel_rooflines case names (with --roofline-only)")
-    ap.add_argument("--roofline-iters", type=int, default=10)
+    ap.add_argument("--roofline-iters", type=int, default=30)
     ap.add_argument("--roofline-warm", type=int, default=3)
     args = ap.parse_args()
     if args.impl == "reference":

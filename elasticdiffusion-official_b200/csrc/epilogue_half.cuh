@@ -27,7 +27,8 @@
 #define ED_HALF_MINB_MULTI 5   // same for the R1 > 1 kernel (measured: 4 -> 0.52, 5 -> 0.56, 6 -> 0.54 of the HBM roofline)
 #endif
 #ifndef ED_HALF_MINB
-#define ED_HALF_MINB 6   // resident 128-thread CTAs per SM the R1 == 1 kernel is compiled for (register cap 65536 / (128 * MINB))
+#define ED_HALF_MINB 7   // resident 128-thread CTAs per SM the R1 == 1 kernel is compiled for (register cap 65536 / (128 * MINB));
+                         // measured plain / +rrg fraction of the HBM roofline: 5 -> 0.78 / 0.73, 6 -> 0.80 / 0.73, 7 -> 0.84 / 0.72, 8 -> 0.80 / 0.67
 #endif
 
 namespace ed {

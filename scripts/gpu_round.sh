@@ -22,6 +22,10 @@ for s in $STAGES; do
     bench5) timeout 600 python bench.py --workload cfg5 --steps 5 --warmup 3 --no-extras > gpurun_out/bench_cfg5_n1.json 2> gpurun_out/bench_cfg5.err; rc=$? ;;
     bench4) timeout 900 python bench.py --workload cfg4 --steps 5 --warmup 3 --no-extras > gpurun_out/bench_cfg4_n1.json 2> gpurun_out/bench_cfg4.err; rc=$? ;;
     bench2) timeout 600 python bench.py --workload cfg2 --steps 5 --warmup 3 --no-extras > gpurun_out/bench_cfg2_n1.json 2> gpurun_out/bench_cfg2.err; rc=$? ;;
+    minbx) for m in 5 7; do ED_NVCC_FLAGS="-DED_HALF_MINB=$m" python -c "import importlib; importlib.import_module('elasticdiffusion-official_b200').native.build(force=True)" && \
+           timeout 240 python bench.py --roofline-only --roofline-iters 30 --roofline-cases 'ed_wave_epilogue+rrg(wave2:R1=1),ed_wave_epilogue(wave2:R1=1)' > gpurun_out/roofline_minb$m.json 2> gpurun_out/roofline_minb$m.err; cat gpurun_out/roofline_minb$m.json; done; rc=$?; \
+           python -c "import importlib; importlib.import_module('elasticdiffusion-official_b200').native.build(force=True)"; \
+           timeout 240 python bench.py --roofline-only --roofline-iters 30 --roofline-cases 'ed_wave_epilogue+rrg(wave2:R1=1),ed_wave_epilogue(wave2:R1=1)' > gpurun_out/roofline_minb6.json; cat gpurun_out/roofline_minb6.json ;;
     minb8) ED_NVCC_FLAGS="-DED_HALF_MINB=8" python -c "import importlib; importlib.import_module('elasticdiffusion-official_b200').native.build(force=True)" && \
            timeout 240 python bench.py --roofline-only --roofline-cases 'ed_wave_epilogue+rrg(wave2:R1=1),ed_wave_epilogue(wave2:R1=1)' > gpurun_out/roofline_minb8.json 2> gpurun_out/roofline_minb8.err; rc=$?; \
            python -c "import importlib; importlib.import_module('elasticdiffusion-official_b200').native.build(force=True)" ;;
