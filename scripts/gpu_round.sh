@@ -19,6 +19,7 @@ for s in $STAGES; do
            --roofline-cases "$CASES" > gpurun_out/ncu.log 2>&1; rc=$? ;;
     e2e) timeout 480 python -m pytest tests/test_gpu_e2e.py tests/test_gpu_zz_staged_in_pipeline.py -x -q > gpurun_out/t_e2e.log 2>&1; rc=$? ;;
     bench) timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench.err; rc=$? ;;
+    benchdrv) timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_n1.json 2> gpurun_out/bench.err; rc=$? ;;
     bench5) timeout 600 python bench.py --workload cfg5 --steps 5 --warmup 3 --no-extras > gpurun_out/bench_cfg5_n1.json 2> gpurun_out/bench_cfg5.err; rc=$? ;;
     bench4) timeout 900 python bench.py --workload cfg4 --steps 5 --warmup 3 --no-extras > gpurun_out/bench_cfg4_n1.json 2> gpurun_out/bench_cfg4.err; rc=$? ;;
     bench2) timeout 600 python bench.py --workload cfg2 --steps 5 --warmup 3 --no-extras > gpurun_out/bench_cfg2_n1.json 2> gpurun_out/bench_cfg2.err; rc=$? ;;
