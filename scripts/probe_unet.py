@@ -78,6 +78,33 @@ def save():
         json.dump(res, f, indent=1)
 
 
+def kernel_table(unet, n, key):
+    """torch.profiler kernel table of ONE eager batch-n forward: kernel count, time in short kernels, top kernels"""
+    x, ehs, kw = inputs(n)
+    with torch.no_grad():
+        for _ in range(2):
+            unet(x, t981, encoder_hidden_states=ehs, **kw)
+        torch.cuda.synchronize()
+        with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+            unet(x, t981, encoder_hidden_states=ehs, **kw)
+            torch.cuda.synchronize()
+    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    dt = lambda e: getattr(e, "device_time", None) or getattr(e, "cuda_time", 0.0)
+    durs = [dt(e) for e in evs]          # us
+    by = {}
+    for e in evs:
+        a = by.setdefault(e.name[:90], [0, 0.0])
+        a[0] += 1
+        a[1] += dt(e)
+    top = sorted(by.items(), key=lambda kv: -kv[1][1])[:25]
+    res[key] = {"kernels": len(durs), "sum_ms": round(sum(durs) / 1e3, 3),
+                "n_under_5us": sum(d < 5 for d in durs), "ms_under_5us": round(sum(d for d in durs if d < 5) / 1e3, 3),
+                "n_under_10us": sum(d < 10 for d in durs), "ms_under_10us": round(sum(d for d in durs if d < 10) / 1e3, 3),
+                "n_under_20us": sum(d < 20 for d in durs), "ms_under_20us": round(sum(d for d in durs if d < 20) / 1e3, 3),
+                "top": [{"name": k, "count": v[0], "total_us": round(v[1], 1), "avg_us": round(v[1] / v[0], 2)} for k, v in top]}
+    print(key, {k: v for k, v in res[key].items() if k != "top"}, flush=True)
+
+
 unet = syn.StandInUNet("XL1.0", device=dev, dtype=torch.bfloat16).eval()
 NS = (1, 2, 3, 4, 5, 6, 8, 10, 20)
 if "--fused-sweep" in sys.argv:      # t(n) with the library's fused GEGLU / GroupNorm(+SiLU) kernels inside the UNet, then plain
@@ -92,6 +119,9 @@ if "--fused-sweep" in sys.argv:      # t(n) with the library's fused GEGLU / Gro
     unet.set_ops(ops.TorchOps)
     res["sweep_torch"] = sweep(unet, (1, 3, 6, 20))
     print("sweep_torch", res["sweep_torch"], flush=True)
+    unet.set_ops(fo)
+    for n in (1, 20):
+        kernel_table(unet, n, f"profile_fused_b{n}")
     save()
     sys.exit(0)
 res["sweep"] = sweep(unet, NS)
@@ -121,29 +151,7 @@ save()
 
 # ---- kernel table of one eager batch-1 / batch-3 forward -------------------------------------------------------------
 for n in (1, 3):
-    x, ehs, kw = inputs(n)
-    with torch.no_grad():
-        for _ in range(2):
-            unet(x, t981, encoder_hidden_states=ehs, **kw)
-        torch.cuda.synchronize()
-        with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
-            unet(x, t981, encoder_hidden_states=ehs, **kw)
-            torch.cuda.synchronize()
-    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
-    dt = lambda e: getattr(e, "device_time", None) or getattr(e, "cuda_time", 0.0)
-    durs = [dt(e) for e in evs]          # us
-    by = {}
-    for e in evs:
-        a = by.setdefault(e.name[:90], [0, 0.0])
-        a[0] += 1
-        a[1] += dt(e)
-    top = sorted(by.items(), key=lambda kv: -kv[1][1])[:25]
-    res[f"profile_b{n}"] = {"kernels": len(durs), "sum_ms": round(sum(durs) / 1e3, 3),
-                            "n_under_5us": sum(d < 5 for d in durs), "ms_under_5us": round(sum(d for d in durs if d < 5) / 1e3, 3),
-                            "n_under_10us": sum(d < 10 for d in durs), "ms_under_10us": round(sum(d for d in durs if d < 10) / 1e3, 3),
-                            "n_under_20us": sum(d < 20 for d in durs), "ms_under_20us": round(sum(d for d in durs if d < 20) / 1e3, 3),
-                            "top": [{"name": k, "count": v[0], "total_us": round(v[1], 1), "avg_us": round(v[1] / v[0], 2)} for k, v in top]}
-    print(f"profile_b{n}", {k: v for k, v in res[f"profile_b{n}"].items() if k != "top"}, flush=True)
+    kernel_table(unet, n, f"profile_b{n}")
 save()
 
 # ---- cudnn.benchmark ---------------------------------------------------------------------------------------------------
