@@ -198,6 +198,52 @@ __global__ void __launch_bounds__(256) bias_add_kernel(T* __restrict__ y, const 
   }
 }
 
+// ---- the same conv epilogue reading the conv output in NHWC (what cuDNN's kernels produce natively) and writing NCHW: fuses
+// the layout transform cuDNN otherwise runs as a separate nhwcToNchw pass.  src element (n, c, p) at (n*HW + p)*C + c, dst
+// (n*C + c)*HW + p.  One CTA = a 64 (pixels) x 64 (channels) tile through shared memory; C % 64 == 0, HW % 64 == 0. ---------
+template <typename T>
+__global__ void __launch_bounds__(256) bias_add_nhwc_kernel(const T* __restrict__ src, T* __restrict__ dst, const T* __restrict__ bias,
+                                                            const T* __restrict__ per_nc, const T* __restrict__ residual, int C, int HW) {
+  __shared__ float tile[64][65];
+  const int n = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
+  const int tid = threadIdx.x;
+  // load: thread -> (pixel, 8-channel vector); 64 x 8 vectors per tile, 2 per thread
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int v = tid + 256 * k, p = v >> 3, cv = v & 7;
+    Pack8<T> pk;
+    pk.load(src + ((long long)n * HW + p0 + p) * C + c0 + cv * 8);
+    float f[8];
+    pk.get(f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tile[p][cv * 8 + j] = f[j];
+  }
+  __syncthreads();
+  // store: thread -> (channel, 8-pixel vector); a warp covers 32 consecutive channels of one pixel vector (conflict-free reads)
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int v = tid + 256 * k, c = v & 63, pv = v >> 6;
+    const long long nc = (long long)n * C + c0 + c;
+    const float b = bias ? to_f32<T>(__ldg(bias + c0 + c)) : 0.f;
+    const float e = per_nc ? to_f32<T>(__ldg(per_nc + nc)) : 0.f;
+    float o[8], rv[8];
+    if (residual) {
+      Pack8<T> r;
+      r.load(residual + nc * HW + p0 + pv * 8);
+      r.get(rv);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = tile[pv * 8 + j][c];
+      if (bias) t = round_to<T>(__fadd_rn(t, b));
+      if (per_nc) t = round_to<T>(__fadd_rn(t, e));
+      if (residual) t = __fadd_rn(t, rv[j]);
+      o[j] = t;
+    }
+    store8<T>(dst + nc * HW + p0 + pv * 8, o);
+  }
+}
+
 // ---- LayerNorm over the last dimension: one warp per row, the row lives in registers (two-pass mean / variance) -------------
 // D % 8 == 0 and D <= 32 * 8 * VPL.  out = (x - mean) * rstd * gamma + beta in float, written as dtype (torch's formula).
 template <typename T, int VPL>
@@ -282,6 +328,23 @@ extern "C" int ed_bias_add(void* y, const void* bias, const void* per_nc, const 
     case ED_F32: bias_add_kernel<float><<<g, 256, 0, stream>>>((float*)y, (const float*)bias, (const float*)per_nc, (const float*)residual, C, HW); break;
     case ED_F16: bias_add_kernel<__half><<<g, 256, 0, stream>>>((__half*)y, (const __half*)bias, (const __half*)per_nc, (const __half*)residual, C, HW); break;
     case ED_BF16: bias_add_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>((__nv_bfloat16*)y, (const __nv_bfloat16*)bias, (const __nv_bfloat16*)per_nc, (const __nv_bfloat16*)residual, C, HW); break;
+    default: return ED_ERR_INVALID;
+  }
+  ED_LAUNCH_CHECK();
+  return ED_OK;
+}
+
+extern "C" int ed_bias_add_nhwc(const void* y_nhwc, void* out_nchw, const void* bias, const void* per_nc, const void* residual, int N,
+                                int C, int HW, int dtype, void* stream_) {
+  if (!y_nhwc || !out_nchw || N <= 0 || C <= 0 || HW <= 0) return ED_ERR_INVALID;
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (C % 64 || HW % 64 || N > 65535 || !al(y_nhwc) || !al(out_nchw) || (residual && !al(residual))) return ED_ERR_UNSUPPORTED;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const dim3 g((unsigned)(HW / 64), (unsigned)(C / 64), (unsigned)N);
+  switch (dtype) {
+    case ED_F32: bias_add_nhwc_kernel<float><<<g, 256, 0, stream>>>((const float*)y_nhwc, (float*)out_nchw, (const float*)bias, (const float*)per_nc, (const float*)residual, C, HW); break;
+    case ED_F16: bias_add_nhwc_kernel<__half><<<g, 256, 0, stream>>>((const __half*)y_nhwc, (__half*)out_nchw, (const __half*)bias, (const __half*)per_nc, (const __half*)residual, C, HW); break;
+    case ED_BF16: bias_add_nhwc_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>((const __nv_bfloat16*)y_nhwc, (__nv_bfloat16*)out_nchw, (const __nv_bfloat16*)bias, (const __nv_bfloat16*)per_nc, (const __nv_bfloat16*)residual, C, HW); break;
     default: return ED_ERR_INVALID;
   }
   ED_LAUNCH_CHECK();

@@ -54,9 +54,11 @@ class TorchOps:
 class FusedOps:
     """Kernels of csrc/unet_ops.cu; `calls` counts how many went to the library / to the torch fall-back."""
 
-    def __init__(self):
+    def __init__(self, channels_last_convs=False):
         self.calls = {"geglu": 0, "group_norm": 0, "layer_norm": 0, "conv_add": 0, "fallback": 0}
         self._ws = {}
+        self._w_cl = {}
+        self.channels_last_convs = channels_last_convs   # convs in cuDNN's native NHWC layout, see _conv_add_nhwc
 
     def _ok(self, x):
         return x.is_cuda and x.is_contiguous() and x.dtype in (torch.float32, torch.float16, torch.bfloat16) and \
@@ -116,6 +118,10 @@ class FusedOps:
                 (conv.bias is not None and conv.bias.dtype != x.dtype)):
             self.calls["fallback"] += 1
             return TorchOps.conv_add(conv, x, per_nc, residual)
+        if self.channels_last_convs and conv.groups == 1 and conv.in_channels % 8 == 0 and conv.out_channels % 64 == 0:
+            out = self._conv_add_nhwc(conv, x, per_nc, residual)
+            if out is not None:
+                return out
         y = F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
         N, C = y.shape[0], y.shape[1]
         HW = y.shape[2] * y.shape[3]
@@ -135,6 +141,28 @@ class FusedOps:
                                               native.dtype_code(y.dtype), native.stream_handle()), "ed_bias_add")
         self.calls["conv_add"] += 1
         return y
+
+    def _conv_add_nhwc(self, conv, x, per_nc, residual):
+        """The conv in cuDNN's native layout: weights kept channels-last ONCE (no per-call weight transform: 1.8 ms of a batch-1
+        SDXL forward), input converted by one torch pass, output left in NHWC and brought back to NCHW by the epilogue kernel
+        itself (ed_bias_add_nhwc) instead of cuDNN's separate nhwcToNchw pass."""
+        key = id(conv)
+        ent = self._w_cl.get(key)
+        if ent is None or ent[0] is not conv.weight or ent[1] != conv.weight._version:
+            ent = self._w_cl[key] = (conv.weight, conv.weight._version, conv.weight.detach().contiguous(memory_format=torch.channels_last))
+        y = F.conv2d(x.contiguous(memory_format=torch.channels_last), ent[2], None, conv.stride, conv.padding, conv.dilation, 1)
+        N, C, H, W = y.shape
+        HW = H * W
+        if not y.is_contiguous(memory_format=torch.channels_last) or HW % 64 or \
+                (per_nc is not None and not (per_nc.is_contiguous() and per_nc.dtype == y.dtype and tuple(per_nc.shape) == (N, C))) or \
+                (residual is not None and not (residual.is_contiguous() and residual.dtype == y.dtype and residual.shape == y.shape)):
+            return None
+        out = torch.empty((N, C, H, W), device=y.device, dtype=y.dtype)
+        native.check(native.lib().ed_bias_add_nhwc(native.ptr(y), native.ptr(out), native.ptr(conv.bias), native.ptr(per_nc),
+                                                   native.ptr(residual), N, C, HW, native.dtype_code(y.dtype), native.stream_handle()),
+                     "ed_bias_add_nhwc")
+        self.calls["conv_add_nhwc"] = self.calls.get("conv_add_nhwc", 0) + 1
+        return out
 
     def group_norm(self, gn, x):
         return self._gn(gn, x, False)

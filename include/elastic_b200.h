@@ -259,6 +259,11 @@ int ed_geglu(const void* x, void* out, int64_t M, int N, int dtype, void* stream
  *           step rounded to `dtype` like the separate torch ops (cuDNN conv -> add_(bias) -> + time-embedding -> + residual):
  *           bit-identical, one vectorised pass instead of two or three unvectorised broadcast adds.  Any of the three may be NULL. */
 int ed_bias_add(void* y, const void* bias, const void* per_nc, const void* residual, int N, int C, int HW, int dtype, void* stream);
+/* ed_bias_add_nhwc: the same epilogue for a conv output left in NHWC memory order (what cuDNN's tensor-core kernels produce when the
+ *           weights are kept channels-last, so that no per-call weight transform runs): reads (N, HW, C), writes contiguous NCHW,
+ *           i.e. it also replaces cuDNN's separate nhwcToNchw pass.  C % 64 == 0, HW % 64 == 0. */
+int ed_bias_add_nhwc(const void* y_nhwc, void* out_nchw, const void* bias, const void* per_nc, const void* residual, int N, int C,
+                     int HW, int dtype, void* stream);
 /* ed_layernorm: LayerNorm over the last dimension of contiguous x (M, D): one warp per row, the row in registers, two-pass
  *           statistics.  D % 8 == 0, D <= 2048, 16-byte aligned pointers; gamma / beta of the same dtype or NULL. */
 int ed_layernorm(const void* x, const void* gamma, const void* beta, void* out, int64_t M, int D, float eps, int dtype, void* stream);

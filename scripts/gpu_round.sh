@@ -34,6 +34,7 @@ for s in $STAGES; do
            timeout 240 python bench.py --roofline-only --roofline-cases 'ed_wave_epilogue+rrg' > gpurun_out/roofline_minbm$m.json 2> gpurun_out/roofline_minbm$m.err; cat gpurun_out/roofline_minbm$m.json; done; rc=$?; \
            python -c "import importlib; importlib.import_module('elasticdiffusion-official_b200').native.build(force=True)" ;;
     benchref) timeout 900 python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; rc=$? ;;
+    probefusedq) timeout 600 python scripts/probe_unet.py --fused-sweep --quick > gpurun_out/probe_unet_fused.log 2>&1; rc=$?; grep -v Warn gpurun_out/probe_unet_fused.log | tail -6 | cut -c1-400 ;;
     probefused) timeout 600 python scripts/probe_unet.py --fused-sweep > gpurun_out/probe_unet_fused.log 2>&1; rc=$?; tail -3 gpurun_out/probe_unet_fused.log ;;
     unetops) timeout 600 python -m pytest tests/test_gpu_unet_ops.py -x -q > gpurun_out/t_unetops.log 2>&1; rc=$?; tail -15 gpurun_out/t_unetops.log ;;
     probe) timeout 600 python scripts/probe_unet.py gpurun_out/probe_unet.json > gpurun_out/probe_unet.log 2>&1; rc=$? ;;

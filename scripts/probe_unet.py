@@ -119,6 +119,16 @@ if "--fused-sweep" in sys.argv:      # t(n) with the library's fused GEGLU / Gro
     unet.set_ops(ops.TorchOps)
     res["sweep_torch"] = sweep(unet, (1, 3, 6, 20))
     print("sweep_torch", res["sweep_torch"], flush=True)
+    fo_cl = ops.FusedOps(channels_last_convs=True)      # convs in cuDNN's native layout (weights channels-last once, fused back-transform)
+    unet.set_ops(fo_cl)
+    res["sweep_fused_nhwc_convs"] = sweep(unet, NS)
+    res["fused_nhwc_calls"] = dict(fo_cl.calls)
+    print("sweep_fused_nhwc_convs", res["sweep_fused_nhwc_convs"], flush=True)
+    for n in (1, 20):
+        kernel_table(unet, n, f"profile_fused_nhwc_b{n}")
+    if "--quick" in sys.argv:
+        save()
+        sys.exit(0)
     unet.set_ops(fo)
     for n in (1, 20):
         kernel_table(unet, n, f"profile_fused_b{n}")

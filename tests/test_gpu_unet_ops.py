@@ -65,6 +65,40 @@ def test_conv_add_is_bit_identical_to_the_separate_torch_ops(dtype, N, Cin, Cout
     assert fo.calls["conv_add"] == 4 and fo.calls["fallback"] == 0
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize("N,Cin,Cout,H,k,stride", [(2, 320, 320, 64, 3, 1), (1, 640, 1280, 32, 3, 1), (3, 960, 640, 32, 1, 1),
+                                                   (2, 320, 320, 64, 3, 2), (1, 1280, 1280, 16, 3, 1)])
+def test_conv_add_in_cudnn_native_layout_matches_the_separate_torch_ops(dtype, N, Cin, Cout, H, k, stride):
+    """channels_last_convs: weights kept channels-last once, conv output left in NHWC, ed_bias_add_nhwc transposes back while it
+    adds.  cuDNN may pick another engine for the other layout, so the conv itself is compared within rounding noise, and
+    the epilogue exactly: ed_bias_add_nhwc(conv_nhwc) == the torch adds applied to the SAME conv output."""
+    import torch.nn.functional as F
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(3)
+    conv = torch.nn.Conv2d(Cin, Cout, k, stride=stride, padding=k // 2).to("cuda", dtype)
+    x = torch.randn(N, Cin, H, H, device="cuda", generator=g).to(dtype)
+    Ho = H // stride
+    temb = torch.randn(N, Cout, device="cuda", generator=g).to(dtype)
+    res = torch.randn(N, Cout, Ho, Ho, device="cuda", generator=g).to(dtype)
+    fo = ops_mod.FusedOps(channels_last_convs=True)
+    with torch.no_grad():
+        y_cl = F.conv2d(x.contiguous(memory_format=torch.channels_last), conv.weight.contiguous(memory_format=torch.channels_last),
+                        None, conv.stride, conv.padding)
+        for per_nc, residual in ((None, None), (temb, None), (None, res), (temb, res)):
+            got = fo.conv_add(conv, x, per_nc=per_nc, residual=residual)
+            assert got.is_contiguous() and got.shape == (N, Cout, Ho, Ho)
+            exact = y_cl.contiguous() + conv.bias[None, :, None, None]
+            if per_nc is not None:
+                exact = exact + per_nc[:, :, None, None]
+            if residual is not None:
+                exact = exact + residual
+            assert torch.equal(got, exact), (got.float() - exact.float()).abs().max().item()
+            want = ops_mod.TorchOps.conv_add(conv, x, per_nc=per_nc, residual=residual)
+            tol = {torch.bfloat16: 2 ** -6, torch.float16: 2 ** -9, torch.float32: 1e-4}[dtype]
+            assert (got.float() - want.float()).abs().max().item() <= tol * want.float().abs().max().item()
+    assert fo.calls.get("conv_add_nhwc", 0) == (4 if (Ho * Ho) % 64 == 0 else 0), fo.calls
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, 2 ** -7), (torch.float16, 2 ** -10), (torch.float32, 2e-6)])
 @pytest.mark.parametrize("shape", [(2, 4096, 640), (3, 1024, 1280), (5, 77, 2048), (7, 64), (1, 9, 1024)])
 def test_layernorm_matches_torch(dtype, tol, shape):
