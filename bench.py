@@ -671,7 +671,7 @@ def main():
         unet.to(memory_format=torch.channels_last)
     # the UNet's GEGLU / GroupNorm(+SiLU) through the library's fused kernels (opt-in feature of the product);
     # the reference legs and the parity checker always run the plain torch formulation of the same weights
-    fused_ops = P.unet_ops.FusedOps(channels_last_convs=os.environ.get("BENCH_NHWC_CONVS", "1") == "1") if args.unet_ops == "fused" else None
+    fused_ops = P.unet_ops.FusedOps(channels_last_convs=os.environ.get("BENCH_NHWC_CONVS", "0") == "1") if args.unet_ops == "fused" else None
 
     def use_ops(fused):
         for m in (unet, cn):

@@ -58,7 +58,10 @@ class FusedOps:
         self.calls = {"geglu": 0, "group_norm": 0, "layer_norm": 0, "conv_add": 0, "fallback": 0}
         self._ws = {}
         self._w_cl = {}
-        self.channels_last_convs = channels_last_convs   # convs in cuDNN's native NHWC layout, see _conv_add_nhwc
+        # convs in cuDNN's native NHWC layout, see _conv_add_nhwc.  Measured on B200 (profiles/r2_probe_unet_fused_nhwc.json): the
+        # SDXL-shaped forward gets faster only at batch <= 2 (15.1 -> 14.4 ms at batch 1) and slower from batch 3 on (163 -> 175 ms at
+        # batch 20: torch's NCHW->NHWC input pass costs more than the per-call weight transform it removes) - off by default
+        self.channels_last_convs = channels_last_convs
 
     def _ok(self, x):
         return x.is_cuda and x.is_contiguous() and x.dtype in (torch.float32, torch.float16, torch.bfloat16) and \
