@@ -536,9 +536,10 @@ def parity_check(ed, unet, workload, device, world, rank, kw, n_steps=2, control
             if i + 1 == n_steps:
                 got["x"] = x.clone()
                 raise _Stop
+        saved_ops = {}
         for mod in (unet, controlnet):             # the checker runs the plain torch formulation of the same weights
             if mod is not None and hasattr(mod, "set_ops"):
-                saved_ops = mod.ops
+                saved_ops[id(mod)] = mod.ops
                 mod.set_ops(pkg().unet_ops.TorchOps)
         m = rp.Models(_NoAutocast(unet), syn.StubVAE().to(device), DDIMRestated(),
                       syn.StubTextEncoder(cross, pooled, device=device), sd, device, vb, projection_dim=pooled,
@@ -549,8 +550,8 @@ def parity_check(ed, unet, workload, device, world, rank, kw, n_steps=2, control
         except _Stop:
             pass
         for mod in (unet, controlnet):
-            if mod is not None and hasattr(mod, "set_ops"):
-                mod.set_ops(saved_ops)
+            if id(mod) in saved_ops:
+                mod.set_ops(saved_ops[id(mod)])
         mse = torch.mean((lat.float() - got["x"].float()) ** 2).item()
         out.update(latent_mse_vs_port=mse, latent_rms=float(got["x"].float().pow(2).mean().sqrt()),
                    ok=bool(mse <= 1e-3) and out.get("ranks_identical", True),

@@ -52,7 +52,9 @@ class TorchOps:
 
 
 class FusedOps:
-    """Kernels of csrc/unet_ops.cu; `calls` counts how many went to the library / to the torch fall-back."""
+    """Kernels of csrc/unet_ops.cu; `calls` counts how many went to the library / to the torch fall-back.
+    One instance serves one stream at a time (the GroupNorm workspace is reused in stream order); use one instance per
+    concurrently running UNet."""
 
     def __init__(self, channels_last_convs=False):
         self.calls = {"geglu": 0, "group_norm": 0, "layer_norm": 0, "conv_add": 0, "fallback": 0}
