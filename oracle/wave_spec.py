@@ -214,7 +214,7 @@ def spec_tile_blend(patches, tiles, B, H, W, core, pad, scale):
 def denoise_wave_form(ed, prompts, negative_prompts="", height=768, width=768, num_inference_steps=50,
                       guidance_scale=10.0, resampling_steps=20, new_p=0.3, rrg_stop_t=0.2, rrg_init_weight=1000,
                       cosine_scale=3.0, repaint_sampling=True, trace=None, condition_image=None,
-                      controlnet_conditioning_scale=1.0):
+                      controlnet_conditioning_scale=1.0, rrg_scherduler_cls=None):
     """The product's wave-batched loop (pipeline.ElasticDiffusion.denoise) with the CUDA ops replaced by the spec
     emulations above; uses the product's geometry, RngLedger and DDIM scalar helpers unchanged."""
     import importlib
@@ -225,7 +225,10 @@ def denoise_wave_form(ed, prompts, negative_prompts="", height=768, width=768, n
     ds = ed.get_downsample_size(height, width)
     ed.default_size = (4 * height, 4 * width)
     T = num_inference_steps
-    rrg_w = pl.CosineScheduler(steps=T - int(T * rrg_stop_t), cosine_scale=cosine_scale, factor=rrg_init_weight)
+    if rrg_scherduler_cls in (None, pl.CosineScheduler):                                       # ed:972-979
+        rrg_w = pl.CosineScheduler(steps=T - int(T * rrg_stop_t), cosine_scale=cosine_scale, factor=rrg_init_weight)
+    else:
+        rrg_w = rrg_scherduler_cls(steps=T - int(T * rrg_stop_t), start_val=rrg_init_weight, stop_val=0)
     prompts = [prompts] if isinstance(prompts, str) else prompts
     negative_prompts = [negative_prompts] * len(prompts) if isinstance(negative_prompts, str) else negative_prompts
     un_text, un_pool = ed.get_text_embeds(negative_prompts)

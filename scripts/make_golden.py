@@ -29,6 +29,12 @@ CASES = {
     # non-default new_p whose threshold 100 * (1 - new_p) = 19.999999999999996 is not representable (float32 compare, ed:542)
     "sd21_512x1024_T3_R3_newp08": ("2.1", 8, dict(height=512, width=1024, num_inference_steps=3, resampling_steps=3,
                                                   new_p=0.8)),
+    # the two other RRG weight schedulers of the public signature (`rrg_scherduler_cls`, ed:73-94, 972-979): 5 steps so that
+    # the weight crosses the `> 10` gate (ed:1062) and the linear ramp / constant plateau differ from the cosine
+    "sd21_512x1024_T5_R2_linear": ("2.1", 4, dict(height=512, width=1024, num_inference_steps=5, resampling_steps=2,
+                                                  rrg_scheduler="linear", rrg_stop_t=0.4)),
+    "xl_1024x2048_T4_R1_const": ("XL1.0", 16, dict(height=1024, width=2048, num_inference_steps=4, resampling_steps=1,
+                                                   rrg_scheduler="const", rrg_stop_t=0.5, rrg_init_weight=400)),
     "xl_1024x2048_T3_R7": ("XL1.0", 16, dict(height=1024, width=2048, num_inference_steps=3, resampling_steps=7)),
     "xl_2048x2048_T2_R2_tiled": ("XL1.0", 16, dict(height=2048, width=2048, num_inference_steps=2, resampling_steps=2,
                                                    tiled_decoder=True)),
@@ -79,7 +85,13 @@ def main():
         o.seed_everything(SEED)
         args = dict(DEFAULTS)
         args.update(kw)
-        imgs, _, latent = run_reference(o, progress=lambda it: it, **args)
+        call = dict(args)
+        sched = call.pop("rrg_scheduler", None)          # stored by NAME in the fixture; the reference takes its own class
+        if sched is not None:
+            from oracle.ref_shim import load_reference_module
+            mod = load_reference_module("elastic_diffusion")
+            call["rrg_scherduler_cls"] = {"linear": mod.LinearScheduler, "const": mod.ConstScheduler, "cosine": mod.CosineScheduler}[sched]
+        imgs, _, latent = run_reference(o, progress=lambda it: it, **call)
         torch.save(dict(sd_version=sd, view_batch_size=vb, seed=SEED, kwargs=args, latent=latent.clone(),
                         image_stats=torch.stack([image_stats(i) for i in imgs]), image_size=imgs[0].size),
                    os.path.join(out_dir, name + ".pt"))

@@ -82,6 +82,15 @@ def oracle_models(sd, vb, device="cpu", controlnet=False):
     return rp.Models(unet, vae, DDIMRestated(), txt, sd, device, vb, projection_dim=proj, controlnet=cn)
 
 
+def scheduler_kw(kw, target):
+    """RRG weight scheduler of a golden (`rrg_scheduler` in its kwargs: "cosine" (default) / "linear" / "const", the three
+    classes of ed:73-107) as the keyword the target takes: the oracle port a name, the product / the reference a class."""
+    name = kw.get("rrg_scheduler", "cosine")
+    if target == "port":
+        return {"rrg_scheduler": name}
+    return {"rrg_scherduler_cls": {"cosine": PKG.CosineScheduler, "linear": PKG.LinearScheduler, "const": PKG.ConstScheduler}[name]}
+
+
 def oracle_kwargs(kw):
     """generate_image kwargs of a golden -> positional meaning for oracle.reference_port.denoise."""
     return dict(prompts=kw["prompts"], negative_prompts=kw["negative_prompts"], height=kw["height"], width=kw["width"],

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from conftest import (PKG, cn_golden_names, condition_tensor, golden_names, load_golden, make_ed, oracle_kwargs,
-                      oracle_models)
+                      oracle_models, scheduler_kw)
 from oracle import reference_port as rp
 
 pytestmark = pytest.mark.gpu
@@ -22,7 +22,7 @@ def test_cuda_path_reproduces_reference_goldens(name):
     ed.rng_device = torch.device("cpu")
     ed.autocast = False                       # goldens are CPU fp32
     ed.seed_everything(g["seed"])
-    lat, _ = ed.denoise(**oracle_kwargs(g["kwargs"]), **NOBAR)
+    lat, _ = ed.denoise(**oracle_kwargs(g["kwargs"]), **scheduler_kw(g["kwargs"], "product"), **NOBAR)
     ref = g["latent"].cuda()
     mse = torch.mean((lat - ref) ** 2).item()
     assert mse < 1e-3, f"latent MSE {mse:.3e} exceeds the north-star tolerance 1e-3"

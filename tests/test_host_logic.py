@@ -7,7 +7,7 @@ import re
 import pytest
 import torch
 
-from conftest import (PKG, ROOT, cn_golden_names, condition_tensor, golden_names, load_golden, make_ed, oracle_kwargs,
+from conftest import (scheduler_kw, PKG, ROOT, cn_golden_names, condition_tensor, golden_names, load_golden, make_ed, oracle_kwargs,
                       oracle_models)
 from oracle import reference_port as rp
 from oracle import wave_spec as ws
@@ -195,7 +195,7 @@ def test_wave_form_reproduces_goldens(name):
     g = load_golden(name)
     ed = make_ed(g["sd_version"], g["view_batch_size"])
     ed.seed_everything(g["seed"])
-    lat = ws.denoise_wave_form(ed, **oracle_kwargs(g["kwargs"]))
+    lat = ws.denoise_wave_form(ed, **oracle_kwargs(g["kwargs"]), **scheduler_kw(g["kwargs"], "product"))
     err = (lat - g["latent"]).abs().max().item()
     # one UNet call per wave instead of one per pass: conv batching may change the last bits on CPU
     assert err <= 2e-5, f"max abs diff {err:.3e}"

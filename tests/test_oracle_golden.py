@@ -3,7 +3,7 @@ reference (scripts/make_golden.py).  This is what pins the oracle."""
 import pytest
 import torch
 
-from conftest import cn_golden_names, condition_tensor, golden_names, load_golden, oracle_kwargs, oracle_models
+from conftest import scheduler_kw, cn_golden_names, condition_tensor, golden_names, load_golden, oracle_kwargs, oracle_models
 from oracle import reference_port as rp
 
 FAST = [n for n in golden_names() if "2048x2048" not in n]
@@ -14,7 +14,7 @@ def test_oracle_reproduces_reference_latent(name):
     g = load_golden(name)
     m = oracle_models(g["sd_version"], g["view_batch_size"])
     rp.seed_all(g["seed"], "cpu")
-    lat = rp.denoise(m, **oracle_kwargs(g["kwargs"]))
+    lat = rp.denoise(m, **oracle_kwargs(g["kwargs"]), **scheduler_kw(g["kwargs"], "port"))
     assert lat.shape == g["latent"].shape
     assert torch.equal(lat, g["latent"]), f"max abs diff {(lat - g['latent']).abs().max().item():.3e}"
 
