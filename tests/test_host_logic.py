@@ -312,3 +312,50 @@ def test_fused_unet_ops_fall_back_to_torch_outside_their_domain():
         unet.set_ops(fo)
         b = unet(*args, **kw)["sample"]
     assert torch.equal(a, b) and fo.calls["fallback"] > 10
+
+
+def test_cli_main_writes_the_reference_s_output_files(tmp_path):
+    """cli.main (the drop-in modules' __main__): parses the reference's flags, constructs the class positionally like the
+    reference, forwards every generate_image keyword and writes `<outdir>/<exp>/<time>_<seed>/{i}.png`, the image-log PNGs and
+    args.txt (ed:1163-1210).  A recording stand-in replaces the class (constructing the real one needs diffusers + weights)."""
+    import importlib
+    from PIL import Image
+    cli = importlib.import_module(PKG.__name__ + ".cli")
+    seen = {}
+
+    class Fake:
+        def __init__(self, device, sd_version, *a, **kw):
+            seen["ctor"] = (str(sd_version), a, kw)
+
+        def seed_everything(self, seed):
+            seen["seed"] = seed
+
+        def generate_image(self, **kw):
+            seen["gen"] = kw
+            img = Image.new("RGB", (8, 8))
+            return [img] * len(kw["prompts"]), {"intermediate_x0_imgs": img, "intermediate_cascade_x0_imgs": {"rrg": img}}
+
+    out = cli.main(Fake, PKG.timelog, argv=["--prompt", "a cat", "--H", "1024", "--W", "2048", "--num_sampled", "2", "--seed", "7",
+                                            "--resampling_steps", "7", "--outdir", str(tmp_path), "--sd_version", "XL1.0"])
+    assert seen["ctor"] == ("XL1.0", (), dict(verbose=False, log_freq=5, view_batch_size=16, low_vram=False)) and seen["seed"] == 7
+    g = seen["gen"]
+    assert (g["prompts"], g["height"], g["width"], g["resampling_steps"], g["rrg_init_weight"], g["cosine_scale"], g["grid"]) == \
+        (["a cat", "a cat"], 1024, 2048, 7, 4000, 10.0, False)
+    files = sorted(os.listdir(out))
+    assert files == ["0.png", "1.png", "args.txt", "intermediate_cascade_x0_imgs_rrg.png", "intermediate_x0_imgs.png"]
+    assert "resampling_steps: 7" in open(os.path.join(out, "args.txt")).read() and out.endswith("_7")
+    assert os.path.basename(os.path.dirname(out)) == "ElasticDiffusion"
+
+
+def test_shard_range_partitions_every_unit_exactly_once():
+    sr = PKG.pipeline.shard_range
+    for n in (1, 5, 6, 20, 26, 64, 225):
+        for world in (1, 2, 3, 4, 8, 16):
+            per = sr(n, world, 0)[0]
+            owned = []
+            for r in range(world):
+                p, lo, hi = sr(n, world, r)
+                assert p == per and 0 <= lo <= hi <= n
+                owned += list(range(lo, hi))
+                assert all(u // per == r for u in range(lo, hi)) or world == 1      # the peer kernels' unit -> rank rule
+            assert owned == list(range(n))
